@@ -1,0 +1,221 @@
+// api.cu -- the extern "C" boundary (include/gof_rasterizer.h): host orchestration of the kernels,
+// replacing CudaRasterizer::Rasterizer::{forward,backward,markVisible} (rasterizer_impl.cu:174-526).
+#include <stdarg.h>
+
+#include "gof_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gof_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* gof_last_error(void) { return g_err; }
+extern "C" int gof_version(void) { return 100; }
+
+static int validate_scene(const gof_scene_t* s) {
+  if (!s) { gof_set_error("scene is NULL"); return GOF_E_INVALID; }
+  if (s->P < 0 || s->width <= 0 || s->height <= 0) { gof_set_error("bad sizes P=%d W=%d H=%d", s->P, s->width, s->height); return GOF_E_INVALID; }
+  if (s->P == 0) return GOF_OK;
+  if (!s->means3D || !s->opacities || !s->viewmatrix || !s->projmatrix || !s->background) {
+    gof_set_error("means3D/opacities/viewmatrix/projmatrix/background must be non-NULL");
+    return GOF_E_INVALID;
+  }
+  // diff_gaussian_rasterization/__init__.py:203-207
+  if ((s->shs == nullptr) == (s->colors_precomp == nullptr)) {
+    gof_set_error("Please provide excatly one of either SHs or precomputed colors!");
+    return GOF_E_INVALID;
+  }
+  if (s->shs) {
+    if (!s->cam_pos) { gof_set_error("cam_pos required with SHs"); return GOF_E_INVALID; }
+    if (s->D < 0 || s->D > 3 || (s->D + 1) * (s->D + 1) > s->M) {
+      gof_set_error("SH degree %d needs %d coefficients, got M=%d", s->D, (s->D + 1) * (s->D + 1), s->M);
+      return GOF_E_INVALID;
+    }
+    if (s->M > 16) { gof_set_error("M=%d SH coefficients unsupported (max 16)", s->M); return GOF_E_INVALID; }
+  }
+  const bool has_sr = s->scales && s->rotations;
+  if (!has_sr && !s->cov3D_precomp) {
+    gof_set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    return GOF_E_INVALID;
+  }
+  // the reference dereferences scales/rotations unconditionally for view2gaussian (forward.cu:334-335,399);
+  // without them a precomputed view2gaussian is the only defined input
+  if (!has_sr && !s->view2gaussian_precomp) {
+    gof_set_error("scales/rotations absent: view2gaussian_precomp is required");
+    return GOF_E_INVALID;
+  }
+  if (s->width > 16 * 65535 || s->height > 16 * 65535) { gof_set_error("image too large"); return GOF_E_INVALID; }
+  return GOF_OK;
+}
+
+extern "C" int gof_rasterize_forward(const gof_scene_t* s, gof_alloc_fn geom_alloc, void* geom_user,
+                                     gof_alloc_fn binning_alloc, void* binning_user, gof_alloc_fn image_alloc,
+                                     void* image_user, float* out_color, int* radii, int* num_rendered,
+                                     void* stream) {
+  int rc = validate_scene(s);
+  if (rc != GOF_OK) return rc;
+  if (!geom_alloc || !binning_alloc || !image_alloc || !num_rendered) {
+    gof_set_error("allocators / num_rendered must be non-NULL");
+    return GOF_E_INVALID;
+  }
+  *num_rendered = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->P == 0) return GOF_OK;   // rasterize_points.cu:85
+  if (!out_color || !radii) { gof_set_error("out_color / radii must be non-NULL"); return GOF_E_INVALID; }
+  const GofView v = gof_make_view(s);
+
+  const GofGeomLayout GL = gof_geom_layout((size_t)s->P);
+  char* geom = (char*)geom_alloc(geom_user, GL.bytes);
+  const GofImageLayout IL = gof_image_layout(s->width, s->height);
+  char* img = (char*)image_alloc(image_user, IL.bytes);
+  if (!geom || !img) { gof_set_error("scratch allocator returned NULL"); return GOF_E_ALLOC; }
+
+  if ((rc = gof_launch_preprocess(s, v, geom, GL, radii, st)) != GOF_OK) return rc;
+  if ((rc = gof_depth_sort_and_offsets(s->P, geom, GL, s->debug != 0, st)) != GOF_OK) return rc;
+
+  // rasterizer_impl.cu:334-340: the instance count sizes the binning buffer (one blocking D2H read)
+  uint32_t R = 0;
+  GOF_CUDA_OK(cudaMemcpyAsync(&R, geom + GL.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  *num_rendered = (int)R;
+
+  const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height);
+  char* bin = (char*)binning_alloc(binning_user, BL.bytes);
+  if (!bin && BL.bytes) { gof_set_error("binning allocator returned NULL"); return GOF_E_ALLOC; }
+
+  if ((rc = gof_bin_tiles(s->P, (size_t)R, v, geom, GL, bin, BL, img, IL, s->debug != 0, st)) != GOF_OK) return rc;
+  if ((rc = gof_launch_render_forward(s, v, geom, GL, bin, BL, img, IL, out_color, st)) != GOF_OK) return rc;
+  return GOF_OK;
+}
+
+extern "C" int gof_rasterize_backward(const gof_scene_t* s, int num_rendered, const int* radii,
+                                      const void* geom_buffer, const void* binning_buffer,
+                                      const void* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+                                      float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                                      float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                      float* dL_dview2gaussian, void* stream) {
+  (void)dL_dconic; (void)dL_dcov3D;
+  int rc = validate_scene(s);
+  if (rc != GOF_OK) return rc;
+  if (s->P == 0) return GOF_OK;   // rasterize_points.cu:172
+  if (!radii || !geom_buffer || !image_buffer || !dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dcolor ||
+      !dL_dmean3D || !dL_dview2gaussian || (num_rendered > 0 && !binning_buffer)) {
+    gof_set_error("backward: NULL argument");
+    return GOF_E_INVALID;
+  }
+  if (s->shs && !dL_dsh) { gof_set_error("backward: dL_dsh required with SHs"); return GOF_E_INVALID; }
+  if (s->scales && s->rotations && (!dL_dscale || !dL_drot)) {
+    gof_set_error("backward: dL_dscale / dL_drot required");
+    return GOF_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const GofView v = gof_make_view(s);
+  const GofGeomLayout GL = gof_geom_layout((size_t)s->P);
+  const GofImageLayout IL = gof_image_layout(s->width, s->height);
+  const GofBinLayout BL = gof_bin_layout((size_t)num_rendered, s->width, s->height);
+  if ((rc = gof_launch_render_backward(s, v, (const char*)geom_buffer, GL, (const char*)binning_buffer, BL,
+                                       (const char*)image_buffer, IL, dL_dpix, dL_dmean2D, dL_dopacity, dL_dcolor,
+                                       dL_dview2gaussian, st)) != GOF_OK)
+    return rc;
+  return gof_launch_preprocess_backward(s, v, (const char*)geom_buffer, GL, radii, dL_dcolor, dL_dview2gaussian,
+                                        dL_dmean3D, dL_dsh, dL_dscale, dL_drot, st);
+}
+
+extern "C" int gof_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                                unsigned char* present, void* stream) {
+  (void)projmatrix;
+  if (P < 0) { gof_set_error("P < 0"); return GOF_E_INVALID; }
+  if (P == 0) return GOF_OK;
+  if (!means3D || !viewmatrix || !present) { gof_set_error("mark_visible: NULL argument"); return GOF_E_INVALID; }
+  return gof_launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+// ---- parity-test export ------------------------------------------------------------------------------
+namespace {
+__global__ void k_export_geom(int P, const int* __restrict__ radii, const GofSplat* __restrict__ splat,
+                              const GofSplatBwd* __restrict__ sb, const unsigned char* __restrict__ clamped,
+                              const uint32_t* __restrict__ tiles, gof_state_view_t o) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const bool vis = radii[i] > 0;
+  GofSplat s;
+  GofSplatBwd b;
+  if (vis) { s = splat[i]; b = sb[i]; }
+  if (o.depths) o.depths[i] = vis ? s.depth : 0.f;
+  if (o.means2D) { o.means2D[2 * i] = vis ? b.mx : 0.f; o.means2D[2 * i + 1] = vis ? b.my : 0.f; }
+  if (o.conic_opacity) {
+    o.conic_opacity[4 * i + 0] = vis ? b.cx : 0.f; o.conic_opacity[4 * i + 1] = vis ? b.cy : 0.f;
+    o.conic_opacity[4 * i + 2] = vis ? b.cz : 0.f; o.conic_opacity[4 * i + 3] = vis ? s.opacity : 0.f;
+  }
+  if (o.rgb) for (int k = 0; k < 3; ++k) o.rgb[3 * i + k] = vis ? s.rgb[k] : 0.f;
+  if (o.view2gaussian) for (int k = 0; k < 10; ++k) o.view2gaussian[10 * i + k] = vis ? s.v2g[k] : 0.f;
+  if (o.clamped) for (int k = 0; k < 3; ++k) o.clamped[3 * i + k] = vis ? ((clamped[i] >> k) & 1) : 0;
+  if (o.tiles_touched) o.tiles_touched[i] = tiles[i];
+}
+
+__global__ void k_export_image(int W, int H, int grid_x, size_t plane, const float* __restrict__ accum,
+                               const uint32_t* __restrict__ nc, gof_state_view_t o) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int tile = (y / 16) * grid_x + (x / 16);
+  const int lx = x & 15, ly = y & 15;
+  const int warp = (ly / 4) * 2 + (lx / 8), lane = (ly & 3) * 8 + (lx & 7);
+  const size_t slot = (size_t)tile * 256 + warp * 32 + lane;
+  const size_t HW = (size_t)W * H, pid = (size_t)y * W + x;
+  if (o.accum_alpha) for (int k = 0; k < 4; ++k) o.accum_alpha[k * HW + pid] = accum[k * plane + slot];
+  if (o.n_contrib) for (int k = 0; k < 2; ++k) o.n_contrib[k * HW + pid] = nc[k * plane + slot];
+}
+}  // namespace
+
+extern "C" int gof_export_state(int P, int width, int height, int num_rendered, const void* geom_buffer,
+                                const void* binning_buffer, const void* image_buffer, const int* radii,
+                                const gof_state_view_t* out, void* stream) {
+  if (!out || P <= 0) { gof_set_error("export_state: bad arguments"); return GOF_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const char* geom = (const char*)geom_buffer;
+  const char* img = (const char*)image_buffer;
+  const char* bin = (const char*)binning_buffer;
+  const GofGeomLayout GL = gof_geom_layout((size_t)P);
+  const GofImageLayout IL = gof_image_layout(width, height);
+  const GofBinLayout BL = gof_bin_layout((size_t)num_rendered, width, height);
+  const int grid_x = (width + 15) / 16, grid_y = (height + 15) / 16;
+  k_export_geom<<<(P + 255) / 256, 256, 0, st>>>(P, radii, (const GofSplat*)(geom + GL.splat),
+                                                 (const GofSplatBwd*)(geom + GL.splat_bwd),
+                                                 (const unsigned char*)(geom + GL.clamped),
+                                                 (const uint32_t*)(geom + GL.tiles), *out);
+  GOF_LAUNCH_CHECK(true, st);
+  if (out->point_list && num_rendered > 0)
+    GOF_CUDA_OK(cudaMemcpyAsync(out->point_list, bin + BL.point_list, (size_t)num_rendered * 4,
+                                cudaMemcpyDeviceToDevice, st));
+  if (out->ranges)
+    GOF_CUDA_OK(cudaMemcpyAsync(out->ranges, img + IL.ranges, (size_t)grid_x * grid_y * 8, cudaMemcpyDeviceToDevice, st));
+  if (out->accum_alpha || out->n_contrib) {
+    dim3 b(16, 16), g((width + 15) / 16, (height + 15) / 16);
+    k_export_image<<<g, b, 0, st>>>(width, height, grid_x, (size_t)grid_x * grid_y * 256,
+                                    (const float*)(img + IL.accum), (const uint32_t*)(img + IL.ncontrib), *out);
+    GOF_LAUNCH_CHECK(true, st);
+  }
+  return GOF_OK;
+}
+
+// ---- not yet built in this revision -------------------------------------------------------------------
+extern "C" int gof_integrate(const gof_scene_t*, int, const float*, gof_alloc_fn, void*, gof_alloc_fn, void*,
+                             gof_alloc_fn, void*, gof_alloc_fn, void*, gof_alloc_fn, void*, float*, int*, float*,
+                             float*, int*, void*) {
+  gof_set_error("gof_integrate: not implemented in this build");
+  return GOF_E_INVALID;
+}
+extern "C" int gof_marching_tets_count(int, const float*, int64_t, const int64_t*, gof_alloc_fn, void*, int64_t*,
+                                       int64_t*, void*) {
+  gof_set_error("gof_marching_tets_count: not implemented in this build");
+  return GOF_E_INVALID;
+}
+extern "C" int gof_marching_tets_emit(int, const float*, int64_t, const int64_t*, const void*, int64_t, int64_t,
+                                      int64_t*, int64_t*, void*) {
+  gof_set_error("gof_marching_tets_emit: not implemented in this build");
+  return GOF_E_INVALID;
+}

@@ -1,0 +1,204 @@
+// gof_common.cuh -- private layouts, launch helpers and error plumbing shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gof_rasterizer.h"
+
+#define GOF_BLOCK_X 16
+#define GOF_BLOCK_Y 16
+#define GOF_BLOCK_SIZE 256
+
+// ---- error plumbing -------------------------------------------------------------------------
+void gof_set_error(const char* fmt, ...);
+
+#define GOF_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      gof_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+      return GOF_E_CUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+// after every launch: always catch launch-configuration errors; with debug also synchronise and
+// surface execution errors (reference: CHECK_CUDA, auxiliary.h:204-211)
+#define GOF_LAUNCH_CHECK(debug, stream)                                                        \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(stream);                      \
+    if (_e != cudaSuccess) {                                                                   \
+      gof_set_error("%s:%d: kernel failed -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return GOF_E_CUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+// ---- per-Gaussian records ---------------------------------------------------------------------
+// One 64-byte, 64-byte-aligned record per Gaussian holds everything the forward blend gathers per
+// (tile,Gaussian) instance: two 32-byte sectors instead of the reference's three unaligned gathers
+// (conic_opacity 16 B + view2gaussian 40 B + rgb 12 B, forward.cu:483-489,561).
+struct __align__(16) GofSplat {
+  float v2g[10];   // view2gaussian quadric: Sigma(6) B(3) C(1)
+  float opacity;   // conic_opacity.w = opacity * coef
+  float rgb[3];    // SH colour (clamped) or colors_precomp
+  float depth;     // view-space z (sort key bits)
+  uint32_t pad;
+};
+static_assert(sizeof(GofSplat) == 64, "GofSplat must be 64 bytes");
+
+// extra per-Gaussian data only the backward blend needs (backward.cu:748-749)
+struct __align__(16) GofSplatBwd {
+  float mx, my;          // means2D
+  float cx, cy, cz;      // 2D conic (used for the densification statistic only)
+  float pad[3];
+};
+static_assert(sizeof(GofSplatBwd) == 32, "GofSplatBwd must be 32 bytes");
+
+// ---- scratch layouts ----------------------------------------------------------------------------
+static inline size_t gof_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define GOF_SORT_ITEMS 16                              // keys per thread in a radix pass
+#define GOF_SORT_CHUNK (GOF_BLOCK_SIZE * GOF_SORT_ITEMS) // keys per block in a radix pass
+#define GOF_RADIX 256
+
+static inline int gof_sort_blocks(size_t n) { return (int)((n + GOF_SORT_CHUNK - 1) / GOF_SORT_CHUNK); }
+
+struct GofGeomLayout {      // "geomBuffer": everything sized by P
+  size_t splat, splat_bwd, rect, tiles, clamped;
+  size_t key_a, key_b, val_a, val_b;   // depth radix sort ping-pong
+  size_t offsets;                      // inclusive scan of tiles_touched in depth order
+  size_t hist;                         // radix block histograms [RADIX][blocks]
+  size_t scan_tmp;                     // scan block sums
+  size_t total;                        // u32 num_rendered (device copy)
+  size_t bytes;
+};
+
+static inline GofGeomLayout gof_geom_layout(size_t P) {
+  GofGeomLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = gof_align_up(o + bytes, 256); return r; };
+  L.splat = take(P * sizeof(GofSplat));
+  L.splat_bwd = take(P * sizeof(GofSplatBwd));
+  L.rect = take(P * 8);
+  L.tiles = take(P * 4);
+  L.clamped = take(P);
+  L.key_a = take(P * 4);
+  L.key_b = take(P * 4);
+  L.val_a = take(P * 4);
+  L.val_b = take(P * 4);
+  L.offsets = take(P * 4);
+  L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(P) + 1) * 4);
+  L.scan_tmp = take((P / 1024 + 2) * 4 + 4096);
+  L.total = take(256);
+  L.bytes = o;
+  return L;
+}
+
+struct GofImageLayout {     // "imgBuffer": per pixel + per tile
+  size_t accum;      // float[4][tiles*256]  tile-major: T, dist1, dist2, raw distortion
+  size_t ncontrib;   // u32  [2][tiles*256]  tile-major: last contributor, median contributor
+  size_t ranges;     // uint2[tiles]
+  size_t bytes;
+};
+
+static inline GofImageLayout gof_image_layout(int W, int H) {
+  const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
+  GofImageLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = gof_align_up(o + bytes, 256); return r; };
+  L.accum = take(tiles * 256 * 4 * 4);
+  L.ncontrib = take(tiles * 256 * 2 * 4);
+  L.ranges = take(tiles * 8);
+  L.bytes = o;
+  return L;
+}
+
+struct GofBinLayout {       // "binningBuffer": everything sized by R = num_rendered
+  size_t key_a, key_b;      // tile ids (u16 when tiles <= 65536, else u32)
+  size_t val_a, val_b;      // Gaussian ids
+  size_t hist;
+  int key_bytes;
+  int passes;               // number of radix passes over the tile id
+  int bits[4];              // digit widths, low digit first
+  size_t point_list;        // offset of the final sorted Gaussian-id list (val_a or val_b)
+  size_t sorted_keys;       // offset of the final sorted tile-id list
+  size_t bytes;
+};
+
+static inline int gof_bits_for(uint32_t n) {   // bits needed to represent values < n
+  int b = 0;
+  while ((1ull << b) < (unsigned long long)n) ++b;
+  return b < 1 ? 1 : b;
+}
+
+static inline GofBinLayout gof_bin_layout(size_t R, int W, int H) {
+  const uint32_t tiles = (uint32_t)((W + 15) / 16) * (uint32_t)((H + 15) / 16);
+  GofBinLayout L;
+  const int nbits = gof_bits_for(tiles);
+  L.key_bytes = tiles <= 65536u ? 2 : 4;
+  L.passes = (nbits + 7) / 8;
+  int rem = nbits;
+  for (int p = 0; p < 4; ++p) L.bits[p] = 0;
+  for (int p = 0; p < L.passes; ++p) {   // split as evenly as possible (e.g. 13 -> 7 + 6)
+    int b = (rem + (L.passes - p) - 1) / (L.passes - p);
+    L.bits[p] = b;
+    rem -= b;
+  }
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = gof_align_up(o + bytes, 256); return r; };
+  L.key_a = take(R * L.key_bytes);
+  L.key_b = take(R * L.key_bytes);
+  L.val_a = take(R * 4);
+  L.val_b = take(R * 4);
+  L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(R) + 1) * 4);
+  L.point_list = (L.passes % 2 == 0) ? L.val_a : L.val_b;
+  L.sorted_keys = (L.passes % 2 == 0) ? L.key_a : L.key_b;
+  L.bytes = o;
+  return L;
+}
+
+// ---- launch prototypes (one per .cu) ----------------------------------------------------------------
+struct GofView {           // host-side derived constants
+  int W, H, grid_x, grid_y, tiles;
+  float focal_x, focal_y;
+};
+
+static inline GofView gof_make_view(const gof_scene_t* s) {
+  GofView v;
+  v.W = s->width; v.H = s->height;
+  v.grid_x = (s->width + 15) / 16; v.grid_y = (s->height + 15) / 16;
+  v.tiles = v.grid_x * v.grid_y;
+  v.focal_y = s->height / (2.0f * s->tan_fovy);   // rasterizer_impl.cu:274-275
+  v.focal_x = s->width / (2.0f * s->tan_fovx);
+  return v;
+}
+
+// preprocess.cu
+int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, const GofGeomLayout& L,
+                          int* radii, cudaStream_t st);
+int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const char* geom,
+                                   const GofGeomLayout& L, const int* radii, const float* dL_dcolor,
+                                   const float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
+                                   float* dL_drot, cudaStream_t st);
+int gof_launch_mark_visible(int P, const float* means3D, const float* vm, unsigned char* present,
+                            cudaStream_t st);
+
+// binning.cu
+int gof_sort_pairs_u32(const uint32_t* keys_in, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a,
+                       uint32_t* vals_b, uint32_t* hist, size_t n, int begin_bit, int end_bit, bool debug,
+                       cudaStream_t st, int* result_in_b);
+int gof_depth_sort_and_offsets(int P, char* geom, const GofGeomLayout& L, bool debug, cudaStream_t st);
+int gof_bin_tiles(int P, size_t R, const GofView& v, char* geom, const GofGeomLayout& GL, char* bin,
+                  const GofBinLayout& BL, char* img, const GofImageLayout& IL, bool debug, cudaStream_t st);
+
+// render_fwd.cu / render_bwd.cu
+int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char* geom,
+                              const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL, char* img,
+                              const GofImageLayout& IL, float* out_color, cudaStream_t st);
+int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, const char* geom,
+                               const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL,
+                               const char* img, const GofImageLayout& IL, const float* dL_dpix,
+                               float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor, float* dL_dv2g,
+                               cudaStream_t st);

@@ -1,0 +1,182 @@
+// render_fwd.cu -- K6: per-tile front-to-back ray-Gaussian compositing (forward.cu:409-612).
+//
+// One 256-thread CTA per 16x16 tile.  Differences from the reference that do not change results:
+//  * a warp covers an 8x4 pixel block (not a 16x2 strip) so the 32 rays of a warp are spatially compact;
+//  * each (tile,Gaussian) instance is gathered as ONE 64-byte record (two sectors) and the gather for batch
+//    i+1 is issued before batch i is blended (register double buffering);
+//  * a conservative single-precision pre-test discards pairs whose alpha is provably < 1/255 before the
+//    reference's double-precision evaluation; every pair that survives is evaluated with exactly the
+//    reference's operation sequence (gof_math.cuh), so accepted alphas are bit-identical.
+#include "gof_common.cuh"
+#include "gof_math.cuh"
+
+namespace {
+
+struct FwdArgs {
+  int W, H, grid_x;
+  float focal_x, focal_y;
+  const uint2* ranges;
+  const uint32_t* point_list;
+  const GofSplat* splat;
+  const float* bg;
+  float* accum;        // [4][tiles*256] tile-major
+  uint32_t* ncontrib;  // [2][tiles*256]
+  float* out_color;    // [9][H][W]
+  size_t plane;        // tiles*256
+};
+
+constexpr int BATCH = GOF_BLOCK_SIZE;
+
+__global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs a) {
+  __shared__ float4 s_rec[BATCH][4];   // 16 KB: the 64-byte records of the current batch
+  __shared__ float s_thr[BATCH];       // ln(1/(255*opacity)) - the largest power that can still be rejected
+
+  const int tile = blockIdx.x;
+  const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t pix_x = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+  const uint32_t pix_y = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+  const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
+  bool done = !inside;
+
+  const float rx = gof_ray(pix_x, a.W, a.focal_x);
+  const float ry = gof_ray(pix_y, a.H, a.focal_y);
+
+  const uint2 range = a.ranges[tile];
+  const int total = (int)(range.y - range.x);
+  const int rounds = (total + BATCH - 1) / BATCH;
+
+  float T = 1.0f;
+  uint32_t contributor = 0, last_contributor = 0, max_contributor = 0xFFFFFFFFu;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, Dm = 0.f, Aacc = 0.f;
+  float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
+
+  // prefetch batch 0
+  float4 nx0, nx1, nx2, nx3;
+  nx0 = nx1 = nx2 = nx3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((int)threadIdx.x < total) {
+    const uint32_t g = a.point_list[range.x + threadIdx.x];
+    const float4* src = reinterpret_cast<const float4*>(a.splat + g);
+    nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2); nx3 = __ldg(src + 3);
+  }
+
+  int toDo = total;
+  for (int i = 0; i < rounds; ++i, toDo -= BATCH) {
+    // forward.cu:475-477: stop when every pixel of the tile is saturated
+    if (__syncthreads_and(done)) break;
+    s_rec[threadIdx.x][0] = nx0; s_rec[threadIdx.x][1] = nx1;
+    s_rec[threadIdx.x][2] = nx2; s_rec[threadIdx.x][3] = nx3;
+    {
+      const float op = nx2.z;   // v2g[8], v2g[9], opacity, rgb0
+      // alpha = op*exp(power) < 1/255  <=>  power < -ln(255*op);   op <= 0 can never contribute
+      s_thr[threadIdx.x] = (op > 0.f) ? (-__logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
+    }
+    __syncthreads();
+    // issue the gather for the next batch; it completes while this batch is blended
+    {
+      const int nxt = (i + 1) * BATCH + (int)threadIdx.x;
+      if (nxt < total) {
+        const uint32_t g = a.point_list[range.x + nxt];
+        const float4* src = reinterpret_cast<const float4*>(a.splat + g);
+        nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2); nx3 = __ldg(src + 3);
+      }
+    }
+
+    const int nb = toDo < BATCH ? toDo : BATCH;
+    for (int j = 0; !done && j < nb; ++j) {
+      contributor++;
+      const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
+      const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+      const GofPair p = gof_pair_geom(v, rx, ry);
+
+      // ---- conservative reject (single precision, error-bounded) ----
+      {
+        const float bh = 0.5f * p.BB;
+        const float qf = bh * bh * __frcp_rn(p.AA);           // ~ BB^2/(4AA), rel. error < 3e-7
+        const float pw = -0.5f * (v[9] - qf);                  // approximate power
+        const float bound = fmaf(fabsf(qf), 3e-7f, pw);        // pw + |error|
+        if (bound < s_thr[j] && fabsf(p.AA) < 1e30f) continue;
+      }
+
+      // ---- exact path: forward.cu:516-541 ----
+      const float t = gof_pair_t(p);
+      if ((double)t <= GOF_NEAR_PLANE_D) continue;
+      const float power = gof_pair_power(p, v[9]);
+      const float alpha = fminf(F_MUL(q2.z, F_EXP(power)), GOF_ALPHA_MAX);
+      if (alpha < GOF_ALPHA_MIN) continue;
+      const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
+      if (test_T < GOF_T_EPS) {
+        done = true;
+        continue;
+      }
+      // forward.cu:543-578
+      const float m = gof_mapped_t(t);
+      const float len = gof_normal_length(p);
+      const float nn0 = F_DIV(p.n0, len), nn1 = F_DIV(p.n1, len), nn2 = F_DIV(p.n2, len);
+      const float A = F_SUB(1.0f, T);
+      const float m2 = F_MUL(m, m);
+      const float err = F_SUB(F_FMA(A, m2, dist2), F_MUL(dist1, F_ADD(m, m)));
+      distortion = F_FMA(T, F_MUL(err, alpha), distortion);
+      dist1 = F_FMA(T, F_MUL(alpha, m), dist1);
+      dist2 = F_FMA(T, F_MUL(m2, alpha), dist2);
+      const float4 q3 = s_rec[j][3];
+      C0 = F_FMA(T, F_MUL(alpha, q2.w), C0);
+      C1 = F_FMA(T, F_MUL(alpha, q3.x), C1);
+      C2 = F_FMA(T, F_MUL(alpha, q3.y), C2);
+      N0 = F_SUB(N0, F_MUL(T, F_MUL(alpha, nn0)));
+      N1 = F_SUB(N1, F_MUL(T, F_MUL(alpha, nn1)));
+      N2 = F_SUB(N2, F_MUL(T, F_MUL(alpha, nn2)));
+      if (T > 0.5f) {
+        Dm = t;
+        max_contributor = contributor;
+      }
+      Aacc = F_FMA(T, alpha, Aacc);
+      T = test_T;
+      last_contributor = contributor;
+    }
+  }
+
+  // forward.cu:584-611
+  const size_t slot = (size_t)tile * 256 + threadIdx.x;
+  a.accum[slot] = T;
+  a.accum[a.plane + slot] = dist1;
+  a.accum[2 * a.plane + slot] = dist2;
+  a.accum[3 * a.plane + slot] = distortion;
+  a.ncontrib[slot] = last_contributor;
+  a.ncontrib[a.plane + slot] = max_contributor;
+  if (inside) {
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t pid = (size_t)pix_y * a.W + pix_x;
+    const float omt = F_SUB(1.0f, T);
+    const float dnorm = (float)D_DIV((double)distortion, D_ADD((double)F_MUL(omt, omt), 1e-7));
+    a.out_color[0 * HW + pid] = F_FMA(T, a.bg[0], C0);
+    a.out_color[1 * HW + pid] = F_FMA(T, a.bg[1], C1);
+    a.out_color[2 * HW + pid] = F_FMA(T, a.bg[2], C2);
+    a.out_color[3 * HW + pid] = N0;
+    a.out_color[4 * HW + pid] = N1;
+    a.out_color[5 * HW + pid] = N2;
+    a.out_color[6 * HW + pid] = Dm;
+    a.out_color[7 * HW + pid] = Aacc;
+    a.out_color[8 * HW + pid] = dnorm;
+  }
+}
+
+}  // namespace
+
+int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char* geom, const GofGeomLayout& GL,
+                              const char* bin, const GofBinLayout& BL, char* img, const GofImageLayout& IL,
+                              float* out_color, cudaStream_t st) {
+  FwdArgs a;
+  a.W = v.W; a.H = v.H; a.grid_x = v.grid_x; a.focal_x = v.focal_x; a.focal_y = v.focal_y;
+  a.ranges = reinterpret_cast<const uint2*>(img + IL.ranges);
+  a.point_list = reinterpret_cast<const uint32_t*>(bin + BL.point_list);
+  a.splat = reinterpret_cast<const GofSplat*>(geom + GL.splat);
+  a.bg = s->background;
+  a.accum = reinterpret_cast<float*>(img + IL.accum);
+  a.ncontrib = reinterpret_cast<uint32_t*>(img + IL.ncontrib);
+  a.out_color = out_color;
+  a.plane = (size_t)v.tiles * 256;
+  k_render_forward<<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a);
+  GOF_LAUNCH_CHECK(s->debug, st);
+  return GOF_OK;
+}

@@ -1,0 +1,261 @@
+"""`_C` -- the four native entry points of the reference's pybind module, bound over the C ABI.
+
+Same names, argument order and return tuples as `diff_gaussian_rasterization._C` of the reference
+(submodules/diff-gaussian-rasterization/ext.cpp:16-19, rasterize_points.cu:36-122, 124-211, 213-232,
+234-343), implemented by ctypes calls into libgof_b200.so (include/gof_rasterizer.h).  torch is used
+only for device memory and the current stream.  There is NO fallback: if the CUDA library cannot be
+loaded the import fails, and CPU tensors are rejected.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgof_b200.so")
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"{_LIB_PATH} is missing: build it with `python gaussian-opacity-fields_b200/build.py` "
+        "(or __graft_entry__.build()). The B200 rasterizer has no CPU / PyTorch fallback."
+    )
+_lib = ctypes.CDLL(_LIB_PATH)
+
+_ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+_fp = ctypes.c_void_p  # device pointers travel as integers
+
+
+class _Scene(ctypes.Structure):
+    _fields_ = [
+        ("P", ctypes.c_int), ("D", ctypes.c_int), ("M", ctypes.c_int),
+        ("width", ctypes.c_int), ("height", ctypes.c_int),
+        ("tan_fovx", ctypes.c_float), ("tan_fovy", ctypes.c_float),
+        ("kernel_size", ctypes.c_float), ("scale_modifier", ctypes.c_float),
+        ("background", _fp), ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp),
+        ("opacities", _fp), ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp),
+        ("view2gaussian_precomp", _fp), ("viewmatrix", _fp), ("projmatrix", _fp),
+        ("cam_pos", _fp), ("subpixel_offset", _fp),
+        ("prefiltered", ctypes.c_int), ("debug", ctypes.c_int),
+    ]
+
+
+class _StateView(ctypes.Structure):
+    _fields_ = [(n, _fp) for n in (
+        "depths", "means2D", "conic_opacity", "rgb", "view2gaussian", "clamped", "tiles_touched",
+        "point_list", "ranges", "accum_alpha", "n_contrib")]
+
+
+_lib.gof_last_error.restype = ctypes.c_char_p
+_lib.gof_rasterize_forward.restype = ctypes.c_int
+_lib.gof_rasterize_forward.argtypes = [
+    ctypes.POINTER(_Scene), _ALLOC_FN, ctypes.c_void_p, _ALLOC_FN, ctypes.c_void_p, _ALLOC_FN, ctypes.c_void_p,
+    _fp, _fp, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+_lib.gof_rasterize_backward.restype = ctypes.c_int
+_lib.gof_rasterize_backward.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int] + [_fp] * 15 + [ctypes.c_void_p]
+_lib.gof_mark_visible.restype = ctypes.c_int
+_lib.gof_mark_visible.argtypes = [ctypes.c_int, _fp, _fp, _fp, _fp, ctypes.c_void_p]
+_lib.gof_integrate.restype = ctypes.c_int
+_lib.gof_integrate.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int, _fp] + [_ALLOC_FN, ctypes.c_void_p] * 5 + \
+    [_fp, _fp, _fp, _fp, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+_lib.gof_export_state.restype = ctypes.c_int
+_lib.gof_export_state.argtypes = [ctypes.c_int] * 4 + [_fp] * 4 + [ctypes.POINTER(_StateView), ctypes.c_void_p]
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"gof_b200 (code {rc}): {_lib.gof_last_error().decode()}")
+
+
+def _ptr(t, dtype=torch.float32, device=None):
+    """Device pointer of a tensor, or None for the reference's "absent" encoding (empty tensor whose
+    data_ptr() is null, rasterize_points.cu:98-115)."""
+    if t is None or t.numel() == 0:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("gof_b200: all non-empty tensor arguments must live on a CUDA device (no CPU path)")
+    if device is not None and t.device != device:
+        raise RuntimeError(f"gof_b200: tensor on {t.device}, expected {device}")
+    if t.dtype != dtype:
+        raise RuntimeError(f"gof_b200: expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _c(t, dtype=torch.float32):
+    """contiguous (keeps a reference alive in the caller's frame)"""
+    if t is None:
+        return None
+    return t.contiguous()
+
+
+class _Scratch:
+    """One opaque uint8 CUDA tensor grown by the library through the allocator callback
+    (resizeFunctional, rasterize_points.cu:28-34)."""
+
+    def __init__(self, device):
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = _ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        # torch's caching allocator returns >= 512-byte aligned blocks
+        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.tensor.device)
+        return self.tensor.data_ptr() if nbytes else 0
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _scene(keep, bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, v2g_precomp,
+           viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset, H, W, sh, degree, campos,
+           prefiltered, debug):
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:61-63
+    dev = means3D.device
+    s = _Scene()
+    s.P = means3D.size(0)
+    s.D = int(degree)
+    s.M = int(sh.size(1)) if (sh is not None and sh.numel() != 0 and sh.size(0) != 0) else 0
+    s.width, s.height = int(W), int(H)
+    s.tan_fovx, s.tan_fovy = float(tan_fovx), float(tan_fovy)
+    s.kernel_size, s.scale_modifier = float(kernel_size), float(scale_modifier)
+    for name, t in (("background", bg), ("means3D", means3D), ("shs", sh), ("colors_precomp", colors),
+                    ("opacities", opacity), ("scales", scales), ("rotations", rotations),
+                    ("cov3D_precomp", cov3D_precomp), ("view2gaussian_precomp", v2g_precomp),
+                    ("viewmatrix", viewmatrix), ("projmatrix", projmatrix), ("cam_pos", campos),
+                    ("subpixel_offset", subpixel_offset)):
+        tc = _c(t)
+        keep.append(tc)
+        setattr(s, name, _ptr(tc, device=dev if s.P else None) if s.P else None)
+    s.prefiltered, s.debug = int(bool(prefiltered)), int(bool(debug))
+    return s
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size,
+                        subpixel_offset, image_height, image_width, sh, degree, campos, prefiltered, debug):
+    """RasterizeGaussiansCUDA (rasterize_points.cu:36-122).
+    Returns (num_rendered, out_color[9,H,W], radii[P], geomBuffer, binningBuffer, imgBuffer)."""
+    keep = []
+    s = _scene(keep, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+               view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
+               image_height, image_width, sh, degree, campos, prefiltered, debug)
+    dev = means3D.device
+    if s.P and not means3D.is_cuda:
+        raise RuntimeError("gof_b200: means3D must be a CUDA tensor (no CPU path)")
+    with torch.cuda.device(dev if means3D.is_cuda else torch.cuda.current_device()):
+        out_color = torch.zeros((9, int(image_height), int(image_width)), dtype=torch.float32, device=dev)
+        radii = torch.zeros((s.P,), dtype=torch.int32, device=dev)
+        sdev = dev if means3D.is_cuda else torch.device("cuda")
+        geom, binning, img = _Scratch(sdev), _Scratch(sdev), _Scratch(sdev)
+        rendered = ctypes.c_int(0)
+        if s.P != 0:
+            _check(_lib.gof_rasterize_forward(ctypes.byref(s), geom.cb, None, binning.cb, None, img.cb, None,
+                                              out_color.data_ptr(), radii.data_ptr(), ctypes.byref(rendered),
+                                              _stream()))
+    return rendered.value, out_color, radii, geom.tensor, binning.tensor, img.tensor
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                 cov3D_precomp, view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                 kernel_size, subpixel_offset, dL_dout_color, sh, degree, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, debug):
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:124-211).  Returns, in the reference's order
+    (:210): (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+    dL_drotations, dL_dview2gaussian)."""
+    P = means3D.size(0)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    keep = []
+    opac_dummy = means3D  # backward never reads opacities; any non-null pointer satisfies validation
+    s = _scene(keep, background, means3D, colors, opac_dummy, scales, rotations, scale_modifier, cov3D_precomp,
+               view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
+               H, W, sh, degree, campos, False, debug)
+    M = s.M
+    o = dict(dtype=means3D.dtype, device=means3D.device)
+    dL_dmeans3D = torch.zeros((P, 3), **o)
+    dL_dmeans2D = torch.zeros((P, 3), **o)
+    dL_dcolors = torch.zeros((P, 3), **o)
+    dL_dconic = torch.zeros((P, 2, 2), **o)
+    dL_dopacity = torch.zeros((P, 1), **o)
+    dL_dcov3D = torch.zeros((P, 6), **o)
+    dL_dsh = torch.zeros((P, M, 3), **o)
+    dL_dscales = torch.zeros((P, 3), **o)
+    dL_drotations = torch.zeros((P, 4), **o)
+    dL_dv2g = torch.zeros((P, 10), **o)
+    if P != 0:
+        g = dL_dout_color.contiguous()
+        rad = radii.contiguous()
+        with torch.cuda.device(means3D.device):
+            _check(_lib.gof_rasterize_backward(
+                ctypes.byref(s), int(R), _ptr(rad, torch.int32), _ptr(geomBuffer, torch.uint8),
+                _ptr(binningBuffer, torch.uint8), _ptr(imageBuffer, torch.uint8), _ptr(g),
+                dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(), dL_dopacity.data_ptr(), dL_dcolors.data_ptr(),
+                dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), _ptr(dL_dsh), dL_dscales.data_ptr(),
+                dL_drotations.data_ptr(), dL_dv2g.data_ptr(), _stream()))
+    return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
+            dL_dv2g)
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """markVisible (rasterize_points.cu:213-232)."""
+    P = means3D.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        m, v, p = means3D.contiguous(), viewmatrix.contiguous(), projmatrix.contiguous()
+        with torch.cuda.device(means3D.device):
+            _check(_lib.gof_mark_visible(P, _ptr(m), _ptr(v), _ptr(p), present.data_ptr(), _stream()))
+    return present
+
+
+def integrate_gaussians_to_points(background, points3D, means3D, colors, opacity, scales, rotations,
+                                  scale_modifier, cov3D_precomp, view2gaussian_precomp, viewmatrix, projmatrix,
+                                  tan_fovx, tan_fovy, kernel_size, subpixel_offset, image_height, image_width, sh,
+                                  degree, campos, prefiltered, debug):
+    """IntegrateGaussiansToPointsCUDA (rasterize_points.cu:234-343).  Returns (num_rendered, out_color,
+    out_alpha_integrated, out_color_integrated, radii, geomBuffer, binningBuffer, imgBuffer)."""
+    if points3D.ndimension() != 2 or points3D.size(1) != 3:
+        raise RuntimeError("points3D must have dimensions (num_points, 3)")
+    keep = []
+    s = _scene(keep, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+               view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
+               image_height, image_width, sh, degree, campos, prefiltered, debug)
+    dev = means3D.device
+    PN = points3D.size(0)
+    out_color = torch.zeros((9, int(image_height), int(image_width)), dtype=torch.float32, device=dev)
+    radii = torch.zeros((s.P,), dtype=torch.int32, device=dev)
+    alpha_int = torch.ones((PN,), dtype=torch.float32, device=dev)
+    color_int = torch.zeros((PN, 3), dtype=torch.float32, device=dev)
+    sdev = dev if means3D.is_cuda else torch.device("cuda")
+    geom, binning, img, pts, pbin = (_Scratch(sdev) for _ in range(5))
+    rendered = ctypes.c_int(0)
+    if s.P != 0 and PN != 0:
+        p3 = points3D.contiguous()
+        with torch.cuda.device(dev):
+            _check(_lib.gof_integrate(ctypes.byref(s), PN, _ptr(p3), geom.cb, None, binning.cb, None, img.cb, None,
+                                      pts.cb, None, pbin.cb, None, out_color.data_ptr(), radii.data_ptr(),
+                                      alpha_int.data_ptr(), color_int.data_ptr(), ctypes.byref(rendered), _stream()))
+    return rendered.value, out_color, alpha_int, color_int, radii, geom.tensor, binning.tensor, img.tensor
+
+
+def export_state(P, W, H, num_rendered, geomBuffer, binningBuffer, imgBuffer, radii):
+    """Parity-test helper (gof_export_state): this library's scratch buffers in the reference's field layout."""
+    dev = radii.device
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    out = {
+        "depths": torch.zeros(P, device=dev), "means2D": torch.zeros(P, 2, device=dev),
+        "conic_opacity": torch.zeros(P, 4, device=dev), "rgb": torch.zeros(P, 3, device=dev),
+        "view2gaussian": torch.zeros(P, 10, device=dev),
+        "clamped": torch.zeros(P, 3, dtype=torch.uint8, device=dev),
+        "tiles_touched": torch.zeros(P, dtype=torch.int32, device=dev),
+        "point_list": torch.zeros(max(num_rendered, 1), dtype=torch.int32, device=dev),
+        "ranges": torch.zeros(tiles, 2, dtype=torch.int32, device=dev),
+        "accum_alpha": torch.zeros(4, H, W, device=dev),
+        "n_contrib": torch.zeros(2, H, W, dtype=torch.int32, device=dev),
+    }
+    sv = _StateView()
+    for k, t in out.items():
+        setattr(sv, k, t.data_ptr())
+    with torch.cuda.device(dev):
+        _check(_lib.gof_export_state(P, W, H, num_rendered, geomBuffer.data_ptr(),
+                                     binningBuffer.data_ptr() if binningBuffer.numel() else None,
+                                     imgBuffer.data_ptr(), radii.data_ptr(), ctypes.byref(sv), _stream()))
+    out["point_list"] = out["point_list"][:num_rendered]
+    return out

@@ -1,0 +1,112 @@
+"""Seeded synthetic workloads: pinhole cameras on a ring and random Gaussians.
+
+Camera matrices are built the way the reference builds them (scene/cameras.py:56-59 with
+utils/graphics_utils.py:38-71): row-vector convention, i.e. the tensors handed to the rasterizer are the
+transposes of the usual column-vector matrices, which the CUDA side reads as column-major.
+Everything is generated on the CPU with an explicit torch.Generator so fixtures are reproducible on any box.
+"""
+import math
+from typing import NamedTuple
+
+import torch
+
+
+class SynthCamera(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    world_view_transform: torch.Tensor   # (4,4) = W2V^T
+    full_proj_transform: torch.Tensor    # (4,4)
+    camera_center: torch.Tensor          # (3,)
+    focal_x: float
+
+
+def _projection(znear, zfar, tan_half_x, tan_half_y):
+    # utils/graphics_utils.py:51-71
+    top, right = tan_half_y * znear, tan_half_x * znear
+    P = torch.zeros(4, 4, dtype=torch.float32)
+    P[0, 0] = 2.0 * znear / (2 * right)
+    P[1, 1] = 2.0 * znear / (2 * top)
+    P[3, 2] = 1.0
+    P[2, 2] = zfar / (zfar - znear)
+    P[2, 3] = -(zfar * znear) / (zfar - znear)
+    return P
+
+
+def make_camera(width, height, view=0, n_views=64, radius=4.0, fovx_deg=60.0, elevation=0.35,
+                znear=0.01, zfar=100.0):
+    """Camera `view` of a ring of `n_views` cameras of radius `radius` looking at the origin."""
+    th = 2.0 * math.pi * (view % n_views) / n_views
+    C = torch.tensor([radius * math.cos(th) * math.cos(elevation), -radius * math.sin(elevation),
+                      radius * math.sin(th) * math.cos(elevation)], dtype=torch.float64)
+    z = -C / C.norm()
+    up = torch.tensor([0.0, -1.0, 0.0], dtype=torch.float64)
+    x = torch.linalg.cross(up, z)
+    x = x / x.norm()
+    y = torch.linalg.cross(z, x)
+    R = torch.stack([x, y, z], dim=1)          # camera-to-world rotation (columns = camera axes)
+    T = -(R.t() @ C)
+    Rt = torch.eye(4, dtype=torch.float64)     # getWorld2View2: [R^T | T]
+    Rt[:3, :3] = R.t()
+    Rt[:3, 3] = T
+    w2v = Rt.to(torch.float32)
+    tan_x = math.tan(math.radians(fovx_deg) / 2.0)
+    tan_y = tan_x * height / width
+    world_view = w2v.t().contiguous()
+    proj = _projection(znear, zfar, tan_x, tan_y).t().contiguous()
+    full = (world_view.unsqueeze(0).bmm(proj.unsqueeze(0))).squeeze(0).contiguous()
+    center = torch.linalg.inv(world_view)[3, :3].contiguous()
+    return SynthCamera(height, width, tan_x, tan_y, world_view, full, center, width / (2.0 * tan_x))
+
+
+def make_gaussians(P, seed, focal_x, sh_degree=3, sigma_px=2.0, sigma_spread=0.7, extent=1.5, radius=4.0):
+    """P random Gaussians: dict of CPU float32 tensors shaped like GaussianModel's activated properties."""
+    g = torch.Generator().manual_seed(int(seed))
+    means3D = (torch.rand(P, 3, generator=g) * 2.0 - 1.0) * extent
+    sig = torch.exp(math.log(sigma_px) + sigma_spread * torch.randn(P, 1, generator=g))
+    aniso = torch.exp(torch.rand(P, 3, generator=g) * math.log(1.0 / 0.3) + math.log(0.3))
+    scales = (sig * radius / focal_x) * aniso
+    rot = torch.randn(P, 4, generator=g)
+    rotations = rot / rot.norm(dim=1, keepdim=True)
+    opacities = torch.sigmoid(1.5 * torch.randn(P, 1, generator=g))
+    M = 16
+    shs = torch.zeros(P, M, 3)
+    shs[:, 0, :] = (torch.rand(P, 3, generator=g) * 2.0 - 1.0) * 1.77
+    shs[:, 1:, :] = 0.1 * torch.randn(P, M - 1, 3, generator=g)
+    return {"means3D": means3D.contiguous(), "scales": scales.contiguous(), "rotations": rotations.contiguous(),
+            "opacities": opacities.contiguous(), "shs": shs.contiguous(), "sh_degree": sh_degree}
+
+
+# the configurations of BASELINE.json / BASELINE.md section 2.2
+CONFIGS = {
+    "C1": dict(P=10_000, width=256, height=256, seed=0),
+    "C2": dict(P=200_000, width=800, height=800, seed=1),
+    "C3": dict(P=1_000_000, width=1920, height=1080, seed=2),
+    "C4": dict(P=2_500_000, width=1920, height=1080, seed=3),
+}
+
+
+def make_scene(name_or_cfg, view=0, device="cpu", **overrides):
+    cfg = dict(CONFIGS[name_or_cfg]) if isinstance(name_or_cfg, str) else dict(name_or_cfg)
+    cfg.update(overrides)
+    cam = make_camera(cfg["width"], cfg["height"], view=view)
+    gs = make_gaussians(cfg["P"], cfg["seed"], cam.focal_x, sh_degree=cfg.get("sh_degree", 3),
+                        sigma_px=cfg.get("sigma_px", 2.0))
+    if device != "cpu":
+        gs = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in gs.items()}
+    return cam, gs
+
+
+def raster_settings(cam, sh_degree, device, kernel_size=0.0, scale_modifier=1.0, bg=(0.0, 0.0, 0.0), debug=False,
+                    settings_cls=None):
+    """GaussianRasterizationSettings exactly as gaussian_renderer/__init__.py:39-54 fills it."""
+    if settings_cls is None:
+        from diff_gaussian_rasterization import GaussianRasterizationSettings as settings_cls
+    return settings_cls(
+        image_height=int(cam.image_height), image_width=int(cam.image_width), tanfovx=cam.tanfovx,
+        tanfovy=cam.tanfovy, kernel_size=kernel_size,
+        subpixel_offset=torch.zeros((cam.image_height, cam.image_width, 2), dtype=torch.float32, device=device),
+        bg=torch.tensor(bg, dtype=torch.float32, device=device), scale_modifier=scale_modifier,
+        viewmatrix=cam.world_view_transform.to(device), projmatrix=cam.full_proj_transform.to(device),
+        sh_degree=sh_degree, campos=cam.camera_center.to(device), prefiltered=False, debug=debug)

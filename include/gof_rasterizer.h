@@ -1,0 +1,156 @@
+/*
+ * gof_rasterizer.h -- C ABI of the B200-native Gaussian-opacity-field rasterizer (libgof_b200.so).
+ *
+ * Drop-in boundary for the reference's `CudaRasterizer::Rasterizer` static interface
+ * (reference: submodules/diff-gaussian-rasterization/cuda_rasterizer/rasterizer.h:20-124) and for the
+ * four pybind entry points built on it (rasterize_points.h:18-98, ext.cpp:16-19).  Plain pointers and
+ * sizes only; no torch / C++ types.  All pointers are DEVICE pointers unless stated otherwise; "absent"
+ * optional inputs are NULL (the reference receives empty CPU tensors whose data_ptr() is nullptr,
+ * rasterize_points.cu:98-115).  All functions return 0 on success, a negative GOF_E_* code on failure;
+ * gof_last_error() gives the message.  Kernels are enqueued on `stream` (a cudaStream_t passed as void*,
+ * NULL = legacy default stream as in the reference, forward.cu:637).
+ *
+ * Scratch memory follows the reference's convention (rasterizer.h:31-56: std::function<char*(size_t)>):
+ * the library calls a caller-provided allocator once per buffer with the exact byte count and the
+ * caller keeps the three opaque buffers alive until backward has run.  Layouts are private to this
+ * library (gof_export_state() converts to the reference's field layout for parity tests).
+ */
+#ifndef GOF_RASTERIZER_H_INCLUDED
+#define GOF_RASTERIZER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GOF_API __attribute__((visibility("default")))
+#else
+#define GOF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOF_OUTPUT_CHANNELS 9   /* auxiliary.h:24 : rgb(3) normal(3) depth alpha distortion */
+#define GOF_TILE 16             /* config.h:16-17 BLOCK_X = BLOCK_Y = 16 */
+
+enum {
+  GOF_OK = 0,
+  GOF_E_INVALID = -1,   /* bad argument combination (mirrors AT_ERROR / std::runtime_error sites) */
+  GOF_E_CUDA = -2,      /* a CUDA call or (with debug=1) a kernel failed */
+  GOF_E_ALLOC = -3      /* the allocator callback returned NULL */
+};
+
+/* rasterizer.h:31-33 : std::function<char*(size_t N)> geometryBuffer / binningBuffer / imageBuffer.
+ * Must return a device pointer aligned to >= 256 bytes valid for `bytes` bytes (bytes may be 0). */
+typedef void* (*gof_alloc_fn)(void* user, size_t bytes);
+
+/* One view + one Gaussian set: the argument list shared by Rasterizer::forward / backward / integrate
+ * (rasterizer_impl.cu:247-272, 409-442, 530-560). */
+typedef struct gof_scene {
+  int P;                /* number of Gaussians                                   (means3D.size(0)) */
+  int D;                /* active SH degree 0..3                                 (raster_settings.sh_degree) */
+  int M;                /* SH coefficients stored per Gaussian, 0 if shs absent  (sh.size(1)) */
+  int width, height;    /* image size in pixels */
+  float tan_fovx, tan_fovy;
+  float kernel_size;    /* 2D mip filter added to the screen-space covariance diagonal */
+  float scale_modifier;
+  const float* background;            /* [3] */
+  const float* means3D;               /* [P,3] */
+  const float* shs;                   /* [P,M,3] or NULL */
+  const float* colors_precomp;        /* [P,3]   or NULL (exactly one of shs / colors_precomp) */
+  const float* opacities;             /* [P] */
+  const float* scales;                /* [P,3]   or NULL */
+  const float* rotations;             /* [P,4] (r,x,y,z), used as given (not re-normalised) or NULL */
+  const float* cov3D_precomp;         /* [P,6]   or NULL */
+  const float* view2gaussian_precomp; /* [P,10]  or NULL */
+  const float* viewmatrix;            /* [16] column-major world->view  */
+  const float* projmatrix;            /* [16] column-major full projection */
+  const float* cam_pos;               /* [3] */
+  const float* subpixel_offset;       /* [H,W,2]; accepted for signature parity, never read by forward */
+  int prefiltered;
+  int debug;                          /* 1: synchronise + check after every launch (auxiliary.h:204-211) */
+} gof_scene_t;
+
+/* Rasterizer::forward (rasterizer_impl.cu:247-405) == _C.rasterize_gaussians.
+ * out_color [9,H,W] and radii [P] must be zero-initialised by the caller (rasterize_points.cu:72-73).
+ * *num_rendered (HOST int) receives the number of (Gaussian,tile) instances. */
+GOF_API int gof_rasterize_forward(const gof_scene_t* scene,
+                          gof_alloc_fn geom_alloc, void* geom_user,
+                          gof_alloc_fn binning_alloc, void* binning_user,
+                          gof_alloc_fn image_alloc, void* image_user,
+                          float* out_color, int* radii, int* num_rendered, void* stream);
+
+/* Rasterizer::backward (rasterizer_impl.cu:409-526) == _C.rasterize_gaussians_backward.
+ * All dL_d* outputs must be zero-initialised by the caller (rasterize_points.cu:161-170).
+ * dL_dconic [P,4] and dL_dcov3D [P,6] are accepted and left untouched (the reference's EWA backward
+ * is disabled, backward.cu:991-1007, 627-630).  dL_dsh may be NULL when M == 0. */
+GOF_API int gof_rasterize_backward(const gof_scene_t* scene, int num_rendered, const int* radii,
+                           const void* geom_buffer, const void* binning_buffer, const void* image_buffer,
+                           const float* dL_dpix,        /* [9,H,W] */
+                           float* dL_dmean2D,           /* [P,3] */
+                           float* dL_dconic,            /* [P,4]  untouched */
+                           float* dL_dopacity,          /* [P] */
+                           float* dL_dcolor,            /* [P,3] */
+                           float* dL_dmean3D,           /* [P,3] */
+                           float* dL_dcov3D,            /* [P,6]  untouched */
+                           float* dL_dsh,               /* [P,M,3] */
+                           float* dL_dscale,            /* [P,3] */
+                           float* dL_drot,              /* [P,4] */
+                           float* dL_dview2gaussian,    /* [P,10] */
+                           void* stream);
+
+/* Rasterizer::integrate (rasterizer_impl.cu:530-792) == _C.integrate_gaussians_to_points.
+ * out_alpha_integrated [PN] must be initialised to 1 and out_color_integrated [PN,3] to 0 by the
+ * caller (rasterize_points.cu:277-278); out_color / radii zero-initialised. */
+GOF_API int gof_integrate(const gof_scene_t* scene, int PN, const float* points3D,
+                  gof_alloc_fn geom_alloc, void* geom_user,
+                  gof_alloc_fn binning_alloc, void* binning_user,
+                  gof_alloc_fn image_alloc, void* image_user,
+                  gof_alloc_fn point_alloc, void* point_user,
+                  gof_alloc_fn point_binning_alloc, void* point_binning_user,
+                  float* out_color, int* radii,
+                  float* out_alpha_integrated, float* out_color_integrated,
+                  int* num_rendered, void* stream);
+
+/* Rasterizer::markVisible (rasterizer_impl.cu:174-186) == _C.mark_visible.  present: [P] bytes (bool). */
+GOF_API int gof_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream);
+
+/* Parity-test helper: converts this library's private scratch layout into the reference's field
+ * layout (rasterizer_impl.h:30-77).  Any output pointer may be NULL.  Per-Gaussian fields of culled
+ * Gaussians (radii == 0) are written as 0. */
+typedef struct gof_state_view {
+  float* depths;            /* [P]     GeometryState::depths */
+  float* means2D;           /* [P,2]   GeometryState::means2D */
+  float* conic_opacity;     /* [P,4]   GeometryState::conic_opacity */
+  float* rgb;               /* [P,3]   GeometryState::rgb */
+  float* view2gaussian;     /* [P,10]  GeometryState::view2gaussian */
+  unsigned char* clamped;   /* [P,3]   GeometryState::clamped */
+  uint32_t* tiles_touched;  /* [P]     GeometryState::tiles_touched */
+  uint32_t* point_list;     /* [R]     BinningState::point_list (sorted Gaussian ids) */
+  uint32_t* ranges;         /* [tiles,2] ImageState::ranges */
+  float* accum_alpha;       /* [4,H,W] ImageState::accum_alpha (T, dist1, dist2, raw distortion) */
+  uint32_t* n_contrib;      /* [2,H,W] ImageState::n_contrib (last, median) */
+} gof_state_view_t;
+
+GOF_API int gof_export_state(int P, int width, int height, int num_rendered,
+                     const void* geom_buffer, const void* binning_buffer, const void* image_buffer,
+                     const int* radii, const gof_state_view_t* out, void* stream);
+
+/* Marching tetrahedra, utils/tetmesh.py:47-138 (_unbatched_marching_tetrahedra), as CUDA.
+ * Two-phase: count (returns sizes on the host), then emit into caller-allocated outputs. */
+GOF_API int gof_marching_tets_count(int num_verts, const float* sdf, int64_t num_tets, const int64_t* tets,
+                            gof_alloc_fn scratch_alloc, void* scratch_user,
+                            int64_t* num_edges_out, int64_t* num_faces_out, void* stream);
+GOF_API int gof_marching_tets_emit(int num_verts, const float* sdf, int64_t num_tets, const int64_t* tets,
+                           const void* scratch, int64_t num_edges, int64_t num_faces,
+                           int64_t* interp_v /* [E,2] */, int64_t* faces /* [F,3] */, void* stream);
+
+GOF_API const char* gof_last_error(void);
+GOF_API int gof_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOF_RASTERIZER_H_INCLUDED */
