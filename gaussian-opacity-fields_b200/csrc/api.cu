@@ -1,8 +1,28 @@
 // api.cu -- the extern "C" boundary (include/gof_rasterizer.h): host orchestration of the kernels,
 // replacing CudaRasterizer::Rasterizer::{forward,backward,markVisible} (rasterizer_impl.cu:174-526).
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include "gof_common.cuh"
+
+// GOF_TRACE=1: host-side phase timings of every forward call on stderr (aux tracing; the reference has none)
+static bool gof_trace_on() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("GOF_TRACE"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+struct GofTrace {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double last = 0;
+  void mark(const char* what) {
+    if (!gof_trace_on()) return;
+    double t = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[gof trace] %-22s +%9.1f us (t=%9.1f us)\n", what, t - last, t);
+    last = t;
+  }
+};
 
 static thread_local char g_err[1024] = "";
 
@@ -68,27 +88,33 @@ extern "C" int gof_rasterize_forward(const gof_scene_t* s, gof_alloc_fn geom_all
   if (!out_color || !radii) { gof_set_error("out_color / radii must be non-NULL"); return GOF_E_INVALID; }
   const GofView v = gof_make_view(s);
 
+  GofTrace tr;
   const GofGeomLayout GL = gof_geom_layout((size_t)s->P);
   char* geom = (char*)geom_alloc(geom_user, GL.bytes);
   const GofImageLayout IL = gof_image_layout(s->width, s->height);
   char* img = (char*)image_alloc(image_user, IL.bytes);
   if (!geom || !img) { gof_set_error("scratch allocator returned NULL"); return GOF_E_ALLOC; }
+  tr.mark("alloc geom+img");
 
   if ((rc = gof_launch_preprocess(s, v, geom, GL, radii, st)) != GOF_OK) return rc;
   if ((rc = gof_depth_sort_and_offsets(s->P, geom, GL, s->debug != 0, st)) != GOF_OK) return rc;
+  tr.mark("launch pre+sort");
 
   // rasterizer_impl.cu:334-340: the instance count sizes the binning buffer (one blocking D2H read)
   uint32_t R = 0;
   GOF_CUDA_OK(cudaMemcpyAsync(&R, geom + GL.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GOF_CUDA_OK(cudaStreamSynchronize(st));
   *num_rendered = (int)R;
+  tr.mark("sync num_rendered");
 
   const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height);
   char* bin = (char*)binning_alloc(binning_user, BL.bytes);
   if (!bin && BL.bytes) { gof_set_error("binning allocator returned NULL"); return GOF_E_ALLOC; }
+  tr.mark("alloc binning");
 
   if ((rc = gof_bin_tiles(s->P, (size_t)R, v, geom, GL, bin, BL, img, IL, s->debug != 0, st)) != GOF_OK) return rc;
   if ((rc = gof_launch_render_forward(s, v, geom, GL, bin, BL, img, IL, out_color, st)) != GOF_OK) return rc;
+  tr.mark("launch bin+render");
   return GOF_OK;
 }
 

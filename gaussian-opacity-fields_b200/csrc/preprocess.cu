@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_preprocess(const PreArgs a) {
     if (alive) {
       // forward.cu:364-372
       const float mid = F_MUL(F_ADD(cov.a, cov.c), 0.5f);
-      const float sq = F_SQRT(fmaxf(F_SUB(F_MUL(mid, mid), cov.det), 0.1f));
+      const float sq = F_SQRT(fmaxf(F_FMA(mid, mid, -cov.det), 0.1f));
       const float lambda1 = F_ADD(mid, sq), lambda2 = F_SUB(mid, sq);
       const float rad_f = ceilf(F_MUL(F_SQRT(fmaxf(lambda1, lambda2)), 3.0f));
       my_radius = gof_f2i_rz(rad_f);

@@ -20,6 +20,7 @@ if not os.path.exists(_LIB_PATH):
     )
 _lib = ctypes.CDLL(_LIB_PATH)
 
+_TRACE = os.environ.get("GOF_TRACE") == "1"
 _ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 _fp = ctypes.c_void_p  # device pointers travel as integers
 
@@ -96,8 +97,16 @@ class _Scratch:
 
     def _alloc(self, _user, nbytes):
         # torch's caching allocator returns >= 512-byte aligned blocks
+        if _TRACE:
+            import time
+            t0 = time.perf_counter()
         self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.tensor.device)
-        return self.tensor.data_ptr() if nbytes else 0
+        p = self.tensor.data_ptr() if nbytes else 0
+        if _TRACE:
+            import sys
+            print(f"[gof trace py] alloc {int(nbytes)} bytes took {1e6 * (time.perf_counter() - t0):.1f} us",
+                  file=sys.stderr, flush=True)
+        return p
 
 
 def _stream():
