@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- training views/sec (rasterizer fwd+bwd) at 1080p on a synthetic 1M-Gaussian scene (BASELINE.json).
+
+One "step" = one view per GPU: rasterize forward (9-channel image) + backward (all parameter gradients), and at
+N > 1 the NCCL all-reduce of the per-Gaussian parameter gradients (59 floats/Gaussian) plus the densification
+statistics.  Workload: config C3 of BASELINE.md (1 000 000 random Gaussians, 1920x1080, sh_degree 3, seed 2; the
+camera moves around a 64-view ring, one new view per step and rank).  `value` is measured with CUDA events with
+all inputs resident in HBM; `e2e` goes through the public drop-in API (GaussianRasterizer + autograd) with the
+step's host inputs (camera + ground-truth image) copied from pinned memory and the loss read back every step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+
+--impl reference times the UNMODIFIED reference extension (oracle/_ref, built from /root/reference for sm_100a by
+oracle/build_ref.sh) on the same GPU through its own entry points; if that build is absent it times the CPU
+restatement of the reference (oracle/) on a bounded sample and says so in `cpu_baseline.kind`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "gaussian-opacity-fields_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import gof_synth  # noqa: E402
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def dist_setup(n):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier_sync(world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------------------
+class Workload:
+    """Device-resident Gaussians + per-view camera tensors for one rank."""
+
+    def __init__(self, cfg_name, dev, rank, world, n_views=64):
+        self.cfg = dict(gof_synth.CONFIGS[cfg_name])
+        self.dev, self.rank, self.world, self.n_views = dev, rank, world, n_views
+        W, H = self.cfg["width"], self.cfg["height"]
+        cam0 = gof_synth.make_camera(W, H, view=0)
+        gs = gof_synth.make_gaussians(self.cfg["P"], self.cfg["seed"], cam0.focal_x)
+        self.gs = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in gs.items()}
+        self.cams = [gof_synth.make_camera(W, H, view=v) for v in range(n_views)]
+        self.W, self.H, self.P = W, H, self.cfg["P"]
+        g = torch.Generator().manual_seed(1234)
+        self.dL_host = torch.randn(9, H, W, generator=g).pin_memory()
+        self.dL = self.dL_host.to(dev)
+        self.gt_host = torch.rand(3, H, W, generator=g).pin_memory()
+        self.bg = torch.zeros(3, device=dev)
+        self.subpix = torch.zeros((H, W, 2), dtype=torch.float32, device=dev)
+        self.empty = torch.Tensor([])
+        self.cam_dev = [(c.world_view_transform.to(dev), c.full_proj_transform.to(dev), c.camera_center.to(dev)) for c in self.cams]
+        self.cam_host = [torch.cat([c.world_view_transform.flatten(), c.full_proj_transform.flatten(), c.camera_center]).pin_memory()
+                         for c in self.cams]
+
+    def view(self, step):
+        return (step * self.world + self.rank) % self.n_views
+
+    def fwd_args(self, v, cam_tensors=None):
+        c = self.cams[v]
+        vm, pm, cp = cam_tensors if cam_tensors is not None else self.cam_dev[v]
+        g = self.gs
+        return (self.bg, g["means3D"], self.empty, g["opacities"], g["scales"], g["rotations"], 1.0, self.empty, self.empty,
+                vm, pm, c.tanfovx, c.tanfovy, 0.0, self.subpix, self.H, self.W, g["shs"], 3, cp, False, False)
+
+
+def bwd_args(fa, radii, geom, R, binning, img, grad):
+    (bg, means3D, colors, opacity, scales, rotations, sm, cov3D, v2g, vm, pm, tfx, tfy, ks, subpix, H, W, sh, deg, campos,
+     pre, dbg) = fa
+    return (bg, means3D, radii, colors, scales, rotations, sm, cov3D, v2g, vm, pm, tfx, tfy, ks, subpix, grad, sh, deg,
+            campos, geom, R, binning, img, dbg)
+
+
+def algorithmic_bytes(P, V, R, N):
+    """bytes one fwd+bwd view must move, and the share of the backward blend kernel."""
+    step = 52 * P + 962 * V + 188 * R + 120 * N
+    render_bwd = 80 * R + 60 * N + 136 * V      # bwd gather + per-pixel reads + one RMW of the 17 accumulators
+    render_fwd = 72 * R + 60 * N
+    return step, render_fwd, render_bwd
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, dev):
+    from diff_gaussian_rasterization import _C, GaussianRasterizer
+    import gof_dp
+
+    wl = Workload(args.config, dev, rank, world)
+    bucket = gof_dp.GradBucket(wl.P, 16, dev)
+    stats = {}
+
+    def step_device(step):
+        v = wl.view(step)
+        fa = wl.fwd_args(v)
+        R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
+        bucket.zero_()
+        grads = _C.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, wl.dL), _out=bucket.views)
+        if world > 1:
+            bucket.all_reduce()
+            gof_dp.all_reduce_densification_stats(gof_dp.densification_stats(grads[0], radii))
+        stats["R"], stats["V"] = R, radii
+        return color
+
+    # ---- kernel-path throughput: inputs resident in HBM, CUDA events, max over ranks --------------------------
+    for s in range(args.warmup):
+        step_device(s)
+    barrier_sync(world)
+    launches0 = _C.launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    _C.profile_reset()
+    _C.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    e0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record()
+    barrier_sync(world)
+    _C.profile_enable(False)
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = _C.launch_count() - launches0
+    prof = _C.profile_report()
+    V = int((stats["V"] > 0).sum())
+    R = int(stats["R"])
+    N = wl.W * wl.H
+
+    # ---- end to end through the public API with host inputs ---------------------------------------------------
+    params = {k: wl.gs[k].detach().clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    h2d = wl.cam_host[0].numel() * 4 + wl.gt_host.numel() * 4
+    cam_buf = torch.empty(35, device=dev)
+    gt_buf = torch.empty(3, wl.H, wl.W, device=dev)
+
+    def step_e2e(step):
+        v = wl.view(step)
+        cam_buf.copy_(wl.cam_host[v], non_blocking=True)          # H2D: this step's camera
+        gt_buf.copy_(wl.gt_host, non_blocking=True)               # H2D: this step's ground-truth image
+        c = wl.cams[v]
+        rs = gof_synth.raster_settings(c, 3, dev)
+        rs = rs._replace(viewmatrix=cam_buf[:16].view(4, 4), projmatrix=cam_buf[16:32].view(4, 4), campos=cam_buf[32:35],
+                         subpixel_offset=wl.subpix, bg=wl.bg)
+        means2D = torch.zeros_like(params["means3D"], requires_grad=True)
+        for p in params.values():
+            p.grad = None
+        img, radii = GaussianRasterizer(rs)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
+                                           shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+        loss = (img[:3] - gt_buf).abs().mean() + 0.05 * (img[3:6] ** 2).mean() + 0.01 * img[6].mean() + 100.0 * img[8].mean()
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([params[k].grad.flatten() for k in ("means3D", "shs", "opacities", "scales", "rotations")])
+            dist.all_reduce(flat)
+        return float(loss.item())                                   # D2H: the loss
+
+    for s in range(max(1, args.warmup // 2)):
+        step_e2e(s)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(args.warmup + s)
+    barrier_sync(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+
+    step_bytes, fwd_bytes, bwd_bytes = algorithmic_bytes(wl.P, V, R, N)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = max(("render_bwd", "render_fwd"), key=lambda k: prof.get(k, (0, 0.0))[1])
+    dom_cnt, dom_ms = prof.get(dom, (1, 0.0))
+    dom_bytes = bwd_bytes if dom == "render_bwd" else fwd_bytes
+    achieved = (dom_bytes / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9) if dom_ms > 0 else None
+
+    line = {
+        "metric": "training views/sec (fwd+bwd) @1080p, 1M Gaussians", "value": world * args.steps / (ms * 1e-3),
+        "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {wl.P} Gaussians, {wl.W}x{wl.H}, sh_degree 3, seed {wl.cfg['seed']}, "
+                               f"64-view ring, 1 view/step/GPU", "visible": V, "num_rendered": R,
+                   "parallelism": f"view-parallel dp{world}" if world > 1 else "single GPU",
+                   "l2": "no explicit flush: a step touches >400 MB (> 126 MB L2) and every step renders a new view"},
+        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                "api": "GaussianRasterizer.forward + autograd backward + L1/normal/depth/distortion loss"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms / max(dom_cnt, 1),
+                     "step_algorithmic_bytes": step_bytes,
+                     "step_frac": step_bytes / ((ms / args.steps) * 1e-3) / 1e9 / peak},
+        "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.config, full=False)
+    return line
+
+
+def cpu_baseline(cfg_name, full):
+    """The reference algorithm on the host cores (oracle/ port, OpenMP): preprocess + binning + sort on the full
+    workload ("the reference's CPU preprocess/sort path"), and one complete fwd+bwd view on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import gof_oracle
+    cfg = dict(gof_synth.CONFIGS[cfg_name])
+    cam, gs = gof_synth.make_scene(cfg_name, view=1)
+    sc = gof_oracle.scene_from_synth(cam, gs)
+    t0 = time.perf_counter()
+    g = gof_oracle.preprocess(sc)
+    t1 = time.perf_counter()
+    R, plist, ranges = gof_oracle.bin_tiles(sc.W, sc.H, g["radii"], g["means2D"], g["depths"], g["tiles_touched"])
+    t2 = time.perf_counter()
+    out = {"kind": "port", "cores": gof_oracle.num_threads(), "host_cpus": os.cpu_count(),
+           "preprocess_s": t1 - t0, "bin_sort_s": t2 - t1, "gaussians_per_s": cfg["P"] / (t1 - t0), "instances_per_s": R / max(t2 - t1, 1e-9)}
+    # bounded sample for the headline unit: the top `rows` pixel rows of the same view, forward + backward
+    rows = cfg["height"] if full else min(cfg["height"], 128)
+    H = sc.H
+    ranges_s = ranges.copy()
+    gx = (sc.W + 15) // 16
+    ranges_s[(rows // 16) * gx:] = 0          # tiles below the sample are empty
+    t3 = time.perf_counter()
+    img, final_T, ncontrib = gof_oracle.render_forward(sc, g, plist, ranges_s)
+    dl = np.random.default_rng(0).standard_normal(img.shape).astype(np.float32)
+    dl[:, rows:, :] = 0
+    d = gof_oracle.render_backward(sc, g, plist, ranges_s, final_T, ncontrib, dl)
+    gof_oracle.preprocess_backward(sc, g["radii"], g["clamped"], d["dL_dcolors"], d["dL_dv2g"])
+    t4 = time.perf_counter()
+    frac = rows / H
+    view_s = (t1 - t0) + (t2 - t1) + (t4 - t3) / frac
+    out.update({"value": 1.0 / view_s, "unit": "views/s",
+                "sample": f"preprocess+bin/sort of the full {cfg_name} view; blend fwd+bwd on the top {rows} of {H} pixel rows "
+                          f"({t4 - t3:.1f} s), extrapolated by rows"})
+    return out
+
+
+def run_reference(args, rank, world, dev):
+    import _util
+    ref = _util.load_ref()
+    if ref is None:
+        cb = cpu_baseline(args.config, full=False)
+        return {"metric": "training views/sec (fwd+bwd) @1080p, 1M Gaussians", "impl": "reference", "value": cb["value"],
+                "unit": "views/s", "n_gpus": 1, "steps": 1, "warmup": 0, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 / cb["value"], "dtype": "f32", "data": "synthetic", "vs_baseline": None,
+                "config": {"workload": args.config, "note": "reference CUDA extension not built here; CPU restatement timed"},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    wl = Workload(args.config, dev, rank, world)
+    st = {}
+
+    def step_device(step):
+        fa = wl.fwd_args(wl.view(step))
+        R, color, radii, geom, binning, img = ref.rasterize_gaussians(*fa)
+        grads = ref.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, wl.dL))
+        if world > 1:
+            flat = torch.cat([grads[i].flatten() for i in (3, 5, 2, 6, 7)])
+            dist.all_reduce(flat)
+        st["R"], st["radii"] = R, radii
+
+    for s in range(args.warmup):
+        step_device(s)
+    barrier_sync(world)
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record()
+    barrier_sync(world)
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    # end to end: same host inputs and loss as our arm, through the reference's own Python-level call sequence
+    cam_buf = torch.empty(35, device=dev)
+    gt_buf = torch.empty(3, wl.H, wl.W, device=dev)
+    h2d = 35 * 4 + wl.gt_host.numel() * 4
+
+    def step_e2e(step):
+        v = wl.view(step)
+        cam_buf.copy_(wl.cam_host[v], non_blocking=True)
+        gt_buf.copy_(wl.gt_host, non_blocking=True)
+        fa = wl.fwd_args(v, (cam_buf[:16].view(4, 4), cam_buf[16:32].view(4, 4), cam_buf[32:35]))
+        R, color, radii, geom, binning, img = ref.rasterize_gaussians(*fa)
+        color.requires_grad_(True)
+        loss = (color[:3] - gt_buf).abs().mean() + 0.05 * (color[3:6] ** 2).mean() + 0.01 * color[6].mean() + 100.0 * color[8].mean()
+        (gcolor,) = torch.autograd.grad(loss, color)
+        grads = ref.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, gcolor))
+        if world > 1:
+            flat = torch.cat([grads[i].flatten() for i in (3, 5, 2, 6, 7)])
+            dist.all_reduce(flat)
+        return float(loss.item())
+
+    for s in range(max(1, args.warmup // 2)):
+        step_e2e(s)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(args.warmup + s)
+    barrier_sync(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    return {
+        "metric": "training views/sec (fwd+bwd) @1080p, 1M Gaussians", "impl": "reference", "value": world * args.steps / (ms * 1e-3),
+        "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {wl.P} Gaussians, {wl.W}x{wl.H}, sh_degree 3", "num_rendered": int(st["R"]),
+                   "visible": int((st["radii"] > 0).sum()),
+                   "reference": "unmodified diff-gaussian-rasterization of GOF compiled for sm_100a (oracle/build_ref.sh), on the GPU"},
+        "cpu_baseline": {"kind": "reference", "cores": 0, "value": world * args.steps / (ms * 1e-3), "unit": "views/s",
+                         "sample": "the reference has no CPU path (rasterize_points.cu:75-79 allocates CUDA tensors); this arm "
+                                   "runs its own CUDA kernels on the same B200"},
+        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "clocks": clocks,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(gof_synth.CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 rasterizer has no CPU path")
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local if world > 1 else 0)
+    line = run_ours(args, rank, world, dev) if args.impl == "ours" else run_reference(args, rank, world, dev)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

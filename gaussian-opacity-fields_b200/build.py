@@ -61,7 +61,7 @@ def build(force=False, verbose=True):
     if failed:
         sys.stderr.write("\n".join(log))
         raise RuntimeError("nvcc failed building libgof_b200.so")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(digest)

@@ -24,6 +24,77 @@ struct GofTrace {
   }
 };
 
+// ---- launch counter + optional per-kernel event timing ----------------------------------------------------
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+namespace {
+struct ProfEntry { const char* name; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+unsigned long long g_launches = 0;
+std::vector<ProfEntry> g_prof_pending;
+std::vector<cudaEvent_t> g_prof_pool;
+std::map<std::string, std::pair<unsigned long long, double>> g_prof_acc;   // name -> (count, ms)
+thread_local ProfEntry g_prof_cur = {nullptr, nullptr, nullptr};
+cudaEvent_t prof_get_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_drain_locked() {
+  for (auto& e : g_prof_pending) {
+    cudaEventSynchronize(e.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    auto& acc = g_prof_acc[e.name];
+    acc.first += 1; acc.second += ms;
+    g_prof_pool.push_back(e.a); g_prof_pool.push_back(e.b);
+  }
+  g_prof_pending.clear();
+}
+}  // namespace
+
+void gof_prof_begin(const char* name, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_launches++;
+  if (!g_prof_on) return;
+  g_prof_cur.name = name; g_prof_cur.a = prof_get_event(); g_prof_cur.b = prof_get_event();
+  cudaEventRecord(g_prof_cur.a, st);
+}
+void gof_prof_end(cudaStream_t st) {
+  if (!g_prof_on || !g_prof_cur.name) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof_cur.b, st);
+  g_prof_pending.push_back(g_prof_cur);
+  g_prof_cur.name = nullptr;
+  if (g_prof_pending.size() > 4096) prof_drain_locked();
+}
+extern "C" unsigned long long gof_launch_count(void) { return g_launches; }
+extern "C" void gof_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!on) prof_drain_locked();
+  g_prof_on = on != 0;
+}
+extern "C" void gof_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  prof_drain_locked();
+  g_prof_acc.clear();
+}
+// writes "name count total_ms\n" lines; returns the number of bytes needed (excluding the terminator)
+extern "C" int gof_profile_report(char* buf, int cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  prof_drain_locked();
+  std::string out;
+  for (auto& kv : g_prof_acc) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %llu %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) { strncpy(buf, out.c_str(), (size_t)cap - 1); buf[cap - 1] = 0; }
+  return (int)out.size();
+}
+
 static thread_local char g_err[1024] = "";
 
 void gof_set_error(const char* fmt, ...) {

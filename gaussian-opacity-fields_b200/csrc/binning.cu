@@ -117,11 +117,11 @@ int scan_u32(Load ld, size_t n, uint32_t* out, uint32_t* tmp, uint32_t* total_ou
     return GOF_OK;
   }
   const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
-  k_scan_reduce<Load><<<nb, SCAN_THREADS, 0, st>>>(ld, n, tmp);
+  GOF_LAUNCH("scan", st, k_scan_reduce<Load><<<nb, SCAN_THREADS, 0, st>>>(ld, n, tmp));
   GOF_LAUNCH_CHECK(debug, st);
-  k_scan_spine<<<1, SCAN_THREADS, 0, st>>>(tmp, nb, total_out);
+  GOF_LAUNCH("scan", st, k_scan_spine<<<1, SCAN_THREADS, 0, st>>>(tmp, nb, total_out));
   GOF_LAUNCH_CHECK(debug, st);
-  k_scan_down<Load, INCLUSIVE><<<nb, SCAN_THREADS, 0, st>>>(ld, n, tmp, out);
+  GOF_LAUNCH("scan", st, k_scan_down<Load, INCLUSIVE><<<nb, SCAN_THREADS, 0, st>>>(ld, n, tmp, out));
   GOF_LAUNCH_CHECK(debug, st);
   return GOF_OK;
 }
@@ -244,11 +244,11 @@ int radix_pass(const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t* vout,
   const int nb = gof_sort_blocks(n);
   const uint32_t mask = (1u << bits) - 1u;
   uint32_t* totals = hist + (size_t)GOF_RADIX * nb;
-  k_radix_hist<KeyT><<<nb, GOF_BLOCK_SIZE, 0, st>>>(kin, n, shift, mask, hist, nb);
+  GOF_LAUNCH("radix_hist", st, k_radix_hist<KeyT><<<nb, GOF_BLOCK_SIZE, 0, st>>>(kin, n, shift, mask, hist, nb));
   GOF_LAUNCH_CHECK(debug, st);
-  k_radix_rowscan<<<(int)mask + 1, SCAN_THREADS, 0, st>>>(hist, nb, totals);
+  GOF_LAUNCH("radix_rowscan", st, k_radix_rowscan<<<(int)mask + 1, SCAN_THREADS, 0, st>>>(hist, nb, totals));
   GOF_LAUNCH_CHECK(debug, st);
-  k_radix_scatter<KeyT><<<nb, GOF_BLOCK_SIZE, 0, st>>>(kin, vin, kout, vout, n, shift, mask, hist, totals, nb);
+  GOF_LAUNCH("radix_scatter", st, k_radix_scatter<KeyT><<<nb, GOF_BLOCK_SIZE, 0, st>>>(kin, vin, kout, vout, n, shift, mask, hist, totals, nb));
   GOF_LAUNCH_CHECK(debug, st);
   return GOF_OK;
 }
@@ -325,9 +325,9 @@ int bin_tiles_t(int P, size_t R, const GofView& v, char* geom, const GofGeomLayo
   uint32_t* hist = reinterpret_cast<uint32_t*>(bin + BL.hist);
   // the depth sort always runs 4 passes: its result is back in the *_a buffers of the geometry state
   const uint32_t* order = reinterpret_cast<const uint32_t*>(geom + GL.val_a);
-  k_emit_instances<KeyT><<<(P + 255) / 256, 256, 0, st>>>(
+  GOF_LAUNCH("emit_instances", st, k_emit_instances<KeyT><<<(P + 255) / 256, 256, 0, st>>>(
       P, order, reinterpret_cast<const uint32_t*>(geom + GL.offsets), reinterpret_cast<const uint2*>(geom + GL.rect),
-      reinterpret_cast<const uint32_t*>(geom + GL.tiles), v.grid_x, ka, va);
+      reinterpret_cast<const uint32_t*>(geom + GL.tiles), v.grid_x, ka, va));
   GOF_LAUNCH_CHECK(debug, st);
   int shift = 0;
   for (int p = 0; p < BL.passes; ++p) {
@@ -338,7 +338,7 @@ int bin_tiles_t(int P, size_t R, const GofView& v, char* geom, const GofGeomLayo
     shift += BL.bits[p];
   }
   const KeyT* sorted = reinterpret_cast<const KeyT*>(bin + BL.sorted_keys);
-  k_tile_ranges<KeyT><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, sorted, ranges);
+  GOF_LAUNCH("tile_ranges", st, k_tile_ranges<KeyT><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, sorted, ranges));
   GOF_LAUNCH_CHECK(debug, st);
   return GOF_OK;
 }

@@ -35,6 +35,19 @@ void gof_set_error(const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
+// ---- launch accounting / per-kernel timing (gof_profile_* in the C ABI) ------------------------------------
+// Every kernel launch goes through GOF_LAUNCH: it bumps the global launch counter and, when profiling is
+// enabled, brackets the launch with CUDA events on the launching stream so bench.py can report per-kernel
+// durations measured live (not under a profiler).
+void gof_prof_begin(const char* name, cudaStream_t st);
+void gof_prof_end(cudaStream_t st);
+#define GOF_LAUNCH(name, st, ...)   \
+  do {                              \
+    gof_prof_begin(name, st);       \
+    __VA_ARGS__;                    \
+    gof_prof_end(st);               \
+  } while (0)
+
 // ---- per-Gaussian records ---------------------------------------------------------------------
 // One 64-byte, 64-byte-aligned record per Gaussian holds everything the forward blend gathers per
 // (tile,Gaussian) instance: two 32-byte sectors instead of the reference's three unaligned gathers

@@ -440,7 +440,7 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
   a.clamped = reinterpret_cast<unsigned char*>(geom + L.clamped);
   a.depth_key = reinterpret_cast<uint32_t*>(geom + L.key_a);
   a.order = reinterpret_cast<uint32_t*>(geom + L.val_a);
-  k_preprocess<<<(s->P + 255) / 256, 256, 0, st>>>(a);
+  GOF_LAUNCH("preprocess_fwd", st, k_preprocess<<<(s->P + 255) / 256, 256, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }
@@ -457,14 +457,14 @@ int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const
   a.scales = s->scales; a.rotations = s->rotations; a.viewmatrix = s->viewmatrix; a.cam_pos = s->cam_pos;
   a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g; a.dL_dmean3D = dL_dmean3D; a.dL_dsh = dL_dsh;
   a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
-  k_preprocess_backward<<<(s->P + 255) / 256, 256, 0, st>>>(a);
+  GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + 255) / 256, 256, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }
 
 int gof_launch_mark_visible(int P, const float* means3D, const float* vm, unsigned char* present,
                             cudaStream_t st) {
-  k_mark_visible<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, vm, present);
+  GOF_LAUNCH("mark_visible", st, k_mark_visible<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, vm, present));
   GOF_LAUNCH_CHECK(false, st);
   return GOF_OK;
 }

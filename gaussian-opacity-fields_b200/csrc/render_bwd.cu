@@ -275,7 +275,7 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, const cha
   a.dL_dpix = dL_dpix;
   a.plane = (size_t)v.tiles * 256;
   a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g;
-  k_render_backward<<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a);
+  GOF_LAUNCH("render_bwd", st, k_render_backward<<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs
       const float nn0 = F_DIV(p.n0, len), nn1 = F_DIV(p.n1, len), nn2 = F_DIV(p.n2, len);
       const float A = F_SUB(1.0f, T);
       const float m2 = F_MUL(m, m);
-      const float err = F_SUB(F_FMA(A, m2, dist2), F_MUL(dist1, F_ADD(m, m)));
+      const float err = F_FMA(-dist1, F_ADD(m, m), F_FMA(A, m2, dist2));
       distortion = F_FMA(T, F_MUL(err, alpha), distortion);
       dist1 = F_FMA(T, F_MUL(alpha, m), dist1);
       dist2 = F_FMA(T, F_MUL(m2, alpha), dist2);
@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs
       C0 = F_FMA(T, F_MUL(alpha, q2.w), C0);
       C1 = F_FMA(T, F_MUL(alpha, q3.x), C1);
       C2 = F_FMA(T, F_MUL(alpha, q3.y), C2);
-      N0 = F_SUB(N0, F_MUL(T, F_MUL(alpha, nn0)));
-      N1 = F_SUB(N1, F_MUL(T, F_MUL(alpha, nn1)));
-      N2 = F_SUB(N2, F_MUL(T, F_MUL(alpha, nn2)));
+      N0 = F_FMA(-T, F_MUL(alpha, nn0), N0);
+      N1 = F_FMA(-T, F_MUL(alpha, nn1), N1);
+      N2 = F_FMA(-T, F_MUL(alpha, nn2), N2);
       if (T > 0.5f) {
         Dm = t;
         max_contributor = contributor;
@@ -176,7 +176,7 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
   a.ncontrib = reinterpret_cast<uint32_t*>(img + IL.ncontrib);
   a.out_color = out_color;
   a.plane = (size_t)v.tiles * 256;
-  k_render_forward<<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a);
+  GOF_LAUNCH("render_fwd", st, k_render_forward<<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }

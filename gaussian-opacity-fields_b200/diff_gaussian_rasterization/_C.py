@@ -166,7 +166,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                  kernel_size, subpixel_offset, dL_dout_color, sh, degree, campos, geomBuffer, R,
-                                 binningBuffer, imageBuffer, debug):
+                                 binningBuffer, imageBuffer, debug, _out=None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:124-211).  Returns, in the reference's order
     (:210): (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
     dL_drotations, dL_dview2gaussian)."""
@@ -179,16 +179,26 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                H, W, sh, degree, campos, False, debug)
     M = s.M
     o = dict(dtype=means3D.dtype, device=means3D.device)
-    dL_dmeans3D = torch.zeros((P, 3), **o)
-    dL_dmeans2D = torch.zeros((P, 3), **o)
-    dL_dcolors = torch.zeros((P, 3), **o)
-    dL_dconic = torch.zeros((P, 2, 2), **o)
-    dL_dopacity = torch.zeros((P, 1), **o)
-    dL_dcov3D = torch.zeros((P, 6), **o)
-    dL_dsh = torch.zeros((P, M, 3), **o)
-    dL_dscales = torch.zeros((P, 3), **o)
-    dL_drotations = torch.zeros((P, 4), **o)
-    dL_dv2g = torch.zeros((P, 10), **o)
+
+    def _z(name, shape):
+        # `_out` (extension, used by gof_dp.GradBucket): pre-zeroed, contiguous destination tensors, e.g. views
+        # of one flat all-reduce buffer, so the backward writes straight into the communication buffer
+        if _out is not None and name in _out:
+            t = _out[name]
+            assert t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.dtype == means3D.dtype
+            return t
+        return torch.zeros(shape, **o)
+
+    dL_dmeans3D = _z("dmeans3D", (P, 3))
+    dL_dmeans2D = _z("dmeans2D", (P, 3))
+    dL_dcolors = _z("dcolors", (P, 3))
+    dL_dconic = None       # the reference allocates (P,2,2) zeros that nothing writes or returns
+    dL_dopacity = _z("dopacity", (P, 1))
+    dL_dcov3D = _z("dcov3D", (P, 6))
+    dL_dsh = _z("dsh", (P, M, 3))
+    dL_dscales = _z("dscales", (P, 3))
+    dL_drotations = _z("drot", (P, 4))
+    dL_dv2g = _z("dv2g", (P, 10))
     if P != 0:
         g = dL_dout_color.contiguous()
         rad = radii.contiguous()
@@ -196,7 +206,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             _check(_lib.gof_rasterize_backward(
                 ctypes.byref(s), int(R), _ptr(rad, torch.int32), _ptr(geomBuffer, torch.uint8),
                 _ptr(binningBuffer, torch.uint8), _ptr(imageBuffer, torch.uint8), _ptr(g),
-                dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(), dL_dopacity.data_ptr(), dL_dcolors.data_ptr(),
+                dL_dmeans2D.data_ptr(), None, dL_dopacity.data_ptr(), dL_dcolors.data_ptr(),
                 dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), _ptr(dL_dsh), dL_dscales.data_ptr(),
                 dL_drotations.data_ptr(), dL_dv2g.data_ptr(), _stream()))
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
@@ -267,4 +277,35 @@ def export_state(P, W, H, num_rendered, geomBuffer, binningBuffer, imgBuffer, ra
                                      binningBuffer.data_ptr() if binningBuffer.numel() else None,
                                      imgBuffer.data_ptr(), radii.data_ptr(), ctypes.byref(sv), _stream()))
     out["point_list"] = out["point_list"][:num_rendered]
+    return out
+
+
+_lib.gof_launch_count.restype = ctypes.c_ulonglong
+_lib.gof_profile_report.restype = ctypes.c_int
+_lib.gof_profile_report.argtypes = [ctypes.c_char_p, ctypes.c_int]
+_lib.gof_profile_enable.argtypes = [ctypes.c_int]
+
+
+def launch_count():
+    """Number of CUDA kernels this library has launched so far (process-wide)."""
+    return int(_lib.gof_launch_count())
+
+
+def profile_enable(on=True):
+    _lib.gof_profile_enable(1 if on else 0)
+
+
+def profile_reset():
+    _lib.gof_profile_reset()
+
+
+def profile_report():
+    """{kernel: (launches, total_ms)} measured with CUDA events on the launching stream while enabled."""
+    n = _lib.gof_profile_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 1)
+    _lib.gof_profile_report(buf, n + 1)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
     return out

@@ -1,0 +1,73 @@
+"""View-parallel helpers: one process per GPU, every rank holds all Gaussians and rasterizes a different view;
+per-Gaussian parameter gradients are summed with ONE all-reduce of a flat buffer.
+
+The reference is single-GPU (its only multi-GPU use is one training job per GPU, scripts/run_mipnerf360.py:20-41),
+so this module is new, not a port.  It uses torch.distributed (NCCL on GPUs, gloo in the CPU tests); the
+rasterizer backward writes its outputs directly into views of the flat buffer (`_out=` of
+`_C.rasterize_gaussians_backward`), so there is no pack/copy step before the collective.
+"""
+import torch
+import torch.distributed as dist
+
+# per-Gaussian parameter gradients that must be reduced across views: 3 + 48 + 1 + 3 + 4 = 59 floats
+_FIELDS = (("dmeans3D", (3,)), ("dsh", None), ("dopacity", (1,)), ("dscales", (3,)), ("drot", (4,)))
+
+
+class GradBucket:
+    """Flat fp32 buffer [sum of fields] with one contiguous, correctly shaped view per gradient tensor."""
+
+    def __init__(self, P, M, device, dtype=torch.float32):
+        self.P, self.M = int(P), int(M)
+        shapes = {}
+        for name, tail in _FIELDS:
+            shapes[name] = (self.P, self.M, 3) if name == "dsh" else (self.P,) + tail
+        self.numel = sum(int(torch.Size(s).numel()) for s in shapes.values())
+        self.flat = torch.zeros(self.numel, dtype=dtype, device=device)
+        self.views = {}
+        off = 0
+        for name, shape in shapes.items():
+            n = int(torch.Size(shape).numel())
+            self.views[name] = self.flat[off:off + n].view(shape)
+            off += n
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce(self, group=None, async_op=False):
+        """Sum over ranks.  World size 1: no-op."""
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return None
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+
+def densification_stats(dmeans2D, radii):
+    """Per-view densification statistics of the reference (scene/gaussian_model.py:709-714): the norm of the
+    signed screen-space gradient, the abs-sum gradient, a visibility count and the radius, as one [P,4]
+    tensor so that a view-parallel step reduces 16 B/Gaussian instead of the raw dL_dmean2D of every view."""
+    vis = radii > 0
+    out = torch.zeros(dmeans2D.shape[0], 4, dtype=torch.float32, device=dmeans2D.device)
+    out[:, 0] = torch.where(vis, torch.linalg.vector_norm(dmeans2D[:, :2], dim=-1), out[:, 0])
+    out[:, 1] = torch.where(vis, torch.linalg.vector_norm(dmeans2D[:, 2:], dim=-1), out[:, 1])
+    out[:, 2] = vis.to(torch.float32)
+    out[:, 3] = radii.to(torch.float32)
+    return out
+
+
+def all_reduce_densification_stats(stats, group=None):
+    """SUM for the two gradient norms and the visibility count, MAX for the radius."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return stats
+    sums = stats[:, :3].contiguous()
+    mx = stats[:, 3].contiguous()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return torch.cat([sums, mx[:, None]], dim=1)
+
+
+def view_for(step, rank, world_size, n_views=64):
+    """Round-robin view schedule: step s gives rank r view (s*world_size + r) mod n_views."""
+    return (step * world_size + rank) % n_views

@@ -147,6 +147,14 @@ GOF_API int gof_marching_tets_emit(int num_verts, const float* sdf, int64_t num_
                            const void* scratch, int64_t num_edges, int64_t num_faces,
                            int64_t* interp_v /* [E,2] */, int64_t* faces /* [F,3] */, void* stream);
 
+/* Launch accounting and live per-kernel timing (CUDA events on the launching stream; not a profiler).
+ * gof_launch_count(): kernels launched by this library so far.  gof_profile_report(): lines of
+ * "<kernel> <launches> <total_ms>" accumulated while profiling was enabled. */
+GOF_API unsigned long long gof_launch_count(void);
+GOF_API void gof_profile_enable(int on);
+GOF_API void gof_profile_reset(void);
+GOF_API int gof_profile_report(char* buf, int cap);
+
 GOF_API const char* gof_last_error(void);
 GOF_API int gof_version(void);
 

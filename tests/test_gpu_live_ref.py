@@ -1,0 +1,55 @@
+"""GPU: differential test against the LIVE unmodified reference extension (oracle/_ref, built from /root/reference
+by oracle/build_ref.sh; travels to the GPU box as a prebuilt .so).  Skipped when that build is absent.
+BASELINE configs 2 and 3 at full size: every integer / index buffer bit-exact, view2gaussian bit-exact, images
+<= 2e-6 relative, gradients within max(1e-4, 4 x the reference's own run-to-run noise measured in the same test)."""
+import pytest
+import torch
+
+import _util
+import gof_synth
+
+pytestmark = pytest.mark.gpu
+NAMES = ["dmeans2D", "dcolors", "dopacity", "dmeans3D", "dcov3D", "dsh", "dscales", "drot", "dv2g"]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    m = _util.load_ref()
+    if m is None:
+        pytest.skip("oracle/_ref/gof_ref_C*.so not built (needs /root/reference at build time)")
+    return m
+
+
+@pytest.mark.parametrize("name,view", [("C2", 3), ("C3", 1)])
+def test_full_size_against_live_reference(ref, name, view):
+    from diff_gaussian_rasterization import _C as ours
+    dev = torch.device("cuda")
+    cam, gs = gof_synth.make_scene(name, view=view)
+    fa = _util.fwd_args(cam, gs, dev)
+    P, W, H = gs["means3D"].shape[0], cam.image_width, cam.image_height
+    Ro, co, rado, geo, bino, imo = ours.rasterize_gaussians(*fa)
+    Rr, cr, radr, ger, binr, imr = ref.rasterize_gaussians(*fa)
+    so = ours.export_state(P, W, H, Ro, geo, bino, imo, rado)
+    sg, si, sb = _util.carve_ref_geom(ger, P), _util.carve_ref_image(imr, W, H), _util.carve_ref_binning(binr, Rr)
+    vis = radr > 0
+    assert Ro == Rr
+    assert torch.equal(rado, radr)
+    assert torch.equal(so["tiles_touched"], sg["tiles_touched"])
+    assert torch.equal(so["point_list"], sb["point_list"])
+    assert torch.equal(so["ranges"], si["ranges"])
+    assert torch.equal(so["n_contrib"], si["n_contrib"])
+    for f in ("depths", "means2D", "conic_opacity", "view2gaussian"):
+        assert torch.equal(so[f][vis].view(torch.int32), sg[f][vis].view(torch.int32)), f
+    assert _util.rel_err(so["rgb"][vis], sg["rgb"][vis])[0] < 5e-7
+    for ch in range(9):
+        assert _util.rel_err(co[ch], cr[ch])[0] < 2e-6, f"channel {ch}"
+    assert torch.equal(co[6], cr[6]) and torch.equal(co[7], cr[7])
+
+    grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(9)).to(dev)
+    go = ours.rasterize_gaussians_backward(*_util.bwd_args(fa, rado, geo, Ro, bino, imo, grad))
+    g1 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    g2 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    for n, a, b, c in zip(NAMES, go, g1, g2):
+        noise = _util.rel_err(c, b)[0]
+        err = _util.rel_err(a, b)[0]
+        assert err <= max(1e-4, 4.0 * noise), f"{n}: ours-vs-ref {err}, ref-vs-ref {noise}"
