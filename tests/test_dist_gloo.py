@@ -36,8 +36,9 @@ def _worker(rank, world, port, q):
     dm2 = torch.randn(P, 3, generator=g)
     radii = torch.randint(0, 5, (P,), generator=g, dtype=torch.int32)
     st = gof_dp.all_reduce_densification_stats(gof_dp.densification_stats(dm2, radii))
-    q.put((rank, {k: v for k, v in local.items()}, {k: v.clone() for k, v in b.views.items()}, dm2, radii, st,
-           [gof_dp.view_for(s, rank, world) for s in range(40)]))
+    # plain numpy in the queue: tensors would be shared by fd and the worker exits before the parent reads
+    q.put((rank, {k: v.numpy().copy() for k, v in local.items()}, {k: v.numpy().copy() for k, v in b.views.items()},
+           dm2.numpy().copy(), radii.numpy().copy(), st.numpy().copy(), [gof_dp.view_for(s, rank, world) for s in range(40)]))
     dist.destroy_process_group()
 
 
@@ -52,6 +53,8 @@ def test_bucket_and_stats_allreduce_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [(r[0], {k: torch.from_numpy(v) for k, v in r[1].items()}, {k: torch.from_numpy(v) for k, v in r[2].items()},
+            torch.from_numpy(r[3]), torch.from_numpy(r[4]), torch.from_numpy(r[5]), r[6]) for r in res]
     for name in res[0][1]:
         total = res[0][1][name] + res[1][1][name]
         for r in range(world):
