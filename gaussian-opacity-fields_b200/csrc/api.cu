@@ -95,6 +95,22 @@ extern "C" int gof_profile_report(char* buf, int cap) {
   return (int)out.size();
 }
 
+static unsigned long long* g_stats_dev = nullptr;
+unsigned long long* gof_stats_buffer() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("GOF_STATS"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (!on) return nullptr;
+  if (!g_stats_dev) { cudaMalloc(&g_stats_dev, 8 * sizeof(unsigned long long)); cudaMemset(g_stats_dev, 0, 8 * sizeof(unsigned long long)); }
+  return g_stats_dev;
+}
+// copies the 8 counters to `out` (host) and clears them; returns 0 if statistics are disabled
+extern "C" __attribute__((visibility("default"))) int gof_stats_read(unsigned long long* out) {
+  if (!gof_stats_buffer()) return 0;
+  cudaMemcpy(out, g_stats_dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_stats_dev, 0, 8 * sizeof(unsigned long long));
+  return 1;
+}
+
 static thread_local char g_err[1024] = "";
 
 void gof_set_error(const char* fmt, ...) {
@@ -235,14 +251,14 @@ extern "C" int gof_mark_visible(int P, const float* means3D, const float* viewma
 namespace {
 __global__ void k_export_geom(int P, const int* __restrict__ radii, const GofSplat* __restrict__ splat,
                               const GofSplatBwd* __restrict__ sb, const unsigned char* __restrict__ clamped,
-                              const uint32_t* __restrict__ tiles, gof_state_view_t o) {
+                              const uint32_t* __restrict__ tiles, const float* __restrict__ depth, gof_state_view_t o) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const bool vis = radii[i] > 0;
   GofSplat s;
   GofSplatBwd b;
   if (vis) { s = splat[i]; b = sb[i]; }
-  if (o.depths) o.depths[i] = vis ? s.depth : 0.f;
+  if (o.depths) o.depths[i] = vis ? depth[i] : 0.f;
   if (o.means2D) { o.means2D[2 * i] = vis ? b.mx : 0.f; o.means2D[2 * i + 1] = vis ? b.my : 0.f; }
   if (o.conic_opacity) {
     o.conic_opacity[4 * i + 0] = vis ? b.cx : 0.f; o.conic_opacity[4 * i + 1] = vis ? b.cy : 0.f;
@@ -283,7 +299,7 @@ extern "C" int gof_export_state(int P, int width, int height, int num_rendered, 
   k_export_geom<<<(P + 255) / 256, 256, 0, st>>>(P, radii, (const GofSplat*)(geom + GL.splat),
                                                  (const GofSplatBwd*)(geom + GL.splat_bwd),
                                                  (const unsigned char*)(geom + GL.clamped),
-                                                 (const uint32_t*)(geom + GL.tiles), *out);
+                                                 (const uint32_t*)(geom + GL.tiles), (const float*)(geom + GL.depth), *out);
   GOF_LAUNCH_CHECK(true, st);
   if (out->point_list && num_rendered > 0)
     GOF_CUDA_OK(cudaMemcpyAsync(out->point_list, bin + BL.point_list, (size_t)num_rendered * 4,

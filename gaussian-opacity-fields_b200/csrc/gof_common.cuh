@@ -48,6 +48,9 @@ void gof_prof_end(cudaStream_t st);
     gof_prof_end(st);               \
   } while (0)
 
+// GOF_STATS=1: device counters of the backward blend (pairs visited / evaluated / contributing); nullptr otherwise
+unsigned long long* gof_stats_buffer();
+
 // ---- per-Gaussian records ---------------------------------------------------------------------
 // One 64-byte, 64-byte-aligned record per Gaussian holds everything the forward blend gathers per
 // (tile,Gaussian) instance: two 32-byte sectors instead of the reference's three unaligned gathers
@@ -56,8 +59,8 @@ struct __align__(16) GofSplat {
   float v2g[10];   // view2gaussian quadric: Sigma(6) B(3) C(1)
   float opacity;   // conic_opacity.w = opacity * coef
   float rgb[3];    // SH colour (clamped) or colors_precomp
-  float depth;     // view-space z (sort key bits)
-  uint32_t pad;
+  uint32_t box_lo; // conservative pixel box of the alpha >= 1/255 region: int16 x0 | int16 y0 << 16
+  uint32_t box_hi; //                                                       int16 x1 | int16 y1 << 16
 };
 static_assert(sizeof(GofSplat) == 64, "GofSplat must be 64 bytes");
 
@@ -79,7 +82,7 @@ static inline size_t gof_align_up(size_t v, size_t a) { return (v + a - 1) / a *
 static inline int gof_sort_blocks(size_t n) { return (int)((n + GOF_SORT_CHUNK - 1) / GOF_SORT_CHUNK); }
 
 struct GofGeomLayout {      // "geomBuffer": everything sized by P
-  size_t splat, splat_bwd, rect, tiles, clamped;
+  size_t splat, splat_bwd, rect, tiles, clamped, depth;
   size_t key_a, key_b, val_a, val_b;   // depth radix sort ping-pong
   size_t offsets;                      // inclusive scan of tiles_touched in depth order
   size_t hist;                         // radix block histograms [RADIX][blocks]
@@ -97,6 +100,7 @@ static inline GofGeomLayout gof_geom_layout(size_t P) {
   L.rect = take(P * 8);
   L.tiles = take(P * 4);
   L.clamped = take(P);
+  L.depth = take(P * 4);
   L.key_a = take(P * 4);
   L.key_b = take(P * 4);
   L.val_a = take(P * 4);

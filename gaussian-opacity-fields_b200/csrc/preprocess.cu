@@ -3,6 +3,8 @@
 // Restates forward.cu:283-404 (preprocessCUDA), backward.cu:593-631 (+ :381-587, :20-139) and
 // rasterizer_impl.cu:54-66 (checkFrustum) of the reference.  One thread per Gaussian, 128-bit loads of the
 // SH rows, one 64-byte GofSplat record out (see gof_common.cuh).
+#include <stdlib.h>
+
 #include "gof_common.cuh"
 #include "gof_math.cuh"
 
@@ -32,6 +34,8 @@ struct PreArgs {
   unsigned char* clamped;
   uint32_t* depth_key;  // depth bits for visible Gaussians, 0xFFFFFFFF otherwise (sorts last)
   uint32_t* order;      // identity permutation, the value array of the depth sort
+  float* depth;         // view-space z of visible Gaussians (parity export)
+  int cull;             // 1: store the conservative alpha-support box, 0: store the whole plane
 };
 
 __global__ void __launch_bounds__(256) k_preprocess(const PreArgs a) {
@@ -137,8 +141,7 @@ __global__ void __launch_bounds__(256) k_preprocess(const PreArgs a) {
     rb.cz = F_MUL(cov.a, det_inv);
     rb.pad[0] = rb.pad[1] = rb.pad[2] = 0.f;
     rec.opacity = F_MUL(cov.coef, a.opacities[idx]);
-    rec.depth = tz;
-    rec.pad = 0u;
+    double lambda_min = 0.0;   // smallest eigenvalue of Sigma = min S^-2; unknown for a precomputed record
     // forward.cu:395-403 (the precomputed record is used with stride 10, rasterizer_impl.cu:379)
     if (a.v2g_precomp == nullptr) {
       float vmat[16];
@@ -146,12 +149,19 @@ __global__ void __launch_bounds__(256) k_preprocess(const PreArgs a) {
       for (int k = 0; k < 16; ++k) vmat[k] = __ldg(vm + k);
       const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
       const GofRot R = gof_quat_to_rot(q.x, q.y, q.z, q.w);
-      gof_view2gaussian(R, a.scales[3 * idx + 0], a.scales[3 * idx + 1], a.scales[3 * idx + 2], px, py, pz, vmat,
-                        rec.v2g);
+      const float sx = a.scales[3 * idx + 0], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
+      gof_view2gaussian(R, sx, sy, sz, px, py, pz, vmat, rec.v2g);
+      const double smax = fmax(fmax(fabs((double)sx), fabs((double)sy)), fabs((double)sz));
+      lambda_min = 1.0 / (smax * smax + 1e-7);
     } else {
 #pragma unroll
       for (int k = 0; k < 10; ++k) rec.v2g[k] = a.v2g_precomp[10 * idx + k];
     }
+    const GofBox box = a.cull ? gof_cull_bbox(rec.v2g, rec.opacity, lambda_min, a.W, a.H, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy)
+                              : gof_full_box();
+    rec.box_lo = ((uint32_t)box.x0 & 0xffffu) | ((uint32_t)box.y0 << 16);
+    rec.box_hi = ((uint32_t)box.x1 & 0xffffu) | ((uint32_t)box.y1 << 16);
+    a.depth[idx] = tz;
     float4* dst = reinterpret_cast<float4*>(a.splat + idx);
     const float4* srcr = reinterpret_cast<const float4*>(&rec);
     dst[0] = srcr[0]; dst[1] = srcr[1]; dst[2] = srcr[2]; dst[3] = srcr[3];
@@ -201,8 +211,11 @@ struct PreBwdArgs {
   float* dL_drot;
 };
 
-// m[c][r] column-major helpers mirroring the glm products used by backward.cu:381-587
-struct M3 { float m[3][3]; };
+// m[c][r] column-major helpers mirroring the glm products used by backward.cu:381-587.  The chain rule through
+// view2gaussian multiplies rounding errors by ~1/scale^2 (the reference's own float results scatter by 1e-3..1e-1
+// between runs), so it is evaluated in double here: the result is the well-conditioned value the reference's
+// float evaluation samples with noise.
+struct M3 { double m[3][3]; };
 
 __device__ __forceinline__ M3 m3_mul(const M3& A, const M3& B) {   // (A*B)[c][r] = sum_k A[k][r]*B[c][k]
   M3 o;
@@ -230,51 +243,55 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
 
   if (a.scales != nullptr && a.rotations != nullptr) {
     // ---- computeView2Gaussian_backward, backward.cu:381-587 ----
-    const float* vm = a.viewmatrix;
+    double vm[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) vm[k] = (double)__ldg(a.viewmatrix + k);
     const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-    const float r = q.x, x = q.y, y = q.z, z = q.w;
-    const float sx = a.scales[3 * idx], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
-    const float* dv = a.dL_dv2g + 10 * (size_t)idx;
+    const double r = q.x, x = q.y, y = q.z, z = q.w;
+    const double sx = a.scales[3 * idx], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
+    const float* dvf = a.dL_dv2g + 10 * (size_t)idx;
+    double dv[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) dv[k] = (double)dvf[k];
 
     M3 R;   // glm::mat3 R(...), column-major constructor
-    R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
-    R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
-    R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+    R.m[0][0] = 1. - 2. * (y * y + z * z); R.m[0][1] = 2. * (x * y - r * z); R.m[0][2] = 2. * (x * z + r * y);
+    R.m[1][0] = 2. * (x * y + r * z); R.m[1][1] = 1. - 2. * (x * x + z * z); R.m[1][2] = 2. * (y * z - r * x);
+    R.m[2][0] = 2. * (x * z - r * y); R.m[2][1] = 2. * (y * z + r * x); R.m[2][2] = 1. - 2. * (x * x + y * y);
 
     // G2V = W2V * G2W; G2W[c] = (R[0][c], R[1][c], R[2][c], 0), G2W[3] = (mean, 1)
-    float G2V[4][3];
+    double G2V[4][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         G2V[c][i] = vm[i] * R.m[0][c] + vm[4 + i] * R.m[1][c] + vm[8 + i] * R.m[2][c];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) G2V[3][i] = vm[i] * mx + vm[4 + i] * my + vm[8 + i] * mz + vm[12 + i];
+    for (int i = 0; i < 3; ++i) G2V[3][i] = vm[i] * (double)mx + vm[4 + i] * (double)my + vm[8 + i] * (double)mz + vm[12 + i];
 
     M3 Rt;   // R_transpose[c][r] = G2V[r][c]
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr) Rt.m[c][rr] = G2V[rr][c];
-    const float t[3] = {G2V[3][0], G2V[3][1], G2V[3][2]};
-    float t2[3];
+    const double t[3] = {G2V[3][0], G2V[3][1], G2V[3][2]};
+    double t2[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) t2[i] = -Rt.m[0][i] * t[0] - Rt.m[1][i] * t[1] - Rt.m[2][i] * t[2];
 
-    const double si[3] = {1.0 / ((double)sx * sx + 1e-7), 1.0 / ((double)sy * sy + 1e-7),
-                          1.0 / ((double)sz * sz + 1e-7)};
+    const double si[3] = {1.0 / (sx * sx + 1e-7), 1.0 / (sy * sy + 1e-7), 1.0 / (sz * sz + 1e-7)};
     M3 SR;   // S_inv_square_R[c][r] = si[r] * Rt[c][r]
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) SR.m[c][rr] = (float)(si[rr] * Rt.m[c][rr]);
+      for (int rr = 0; rr < 3; ++rr) SR.m[c][rr] = si[rr] * Rt.m[c][rr];
 
     M3 dS;   // symmetric
-    dS.m[0][0] = dv[0]; dS.m[0][1] = 0.5f * dv[1]; dS.m[0][2] = 0.5f * dv[2];
-    dS.m[1][0] = 0.5f * dv[1]; dS.m[1][1] = dv[3]; dS.m[1][2] = 0.5f * dv[4];
-    dS.m[2][0] = 0.5f * dv[2]; dS.m[2][1] = 0.5f * dv[4]; dS.m[2][2] = dv[5];
-    const float dB[3] = {dv[6], dv[7], dv[8]};
-    const float dC = dv[9];
+    dS.m[0][0] = dv[0]; dS.m[0][1] = 0.5 * dv[1]; dS.m[0][2] = 0.5 * dv[2];
+    dS.m[1][0] = 0.5 * dv[1]; dS.m[1][1] = dv[3]; dS.m[1][2] = 0.5 * dv[4];
+    dS.m[2][0] = 0.5 * dv[2]; dS.m[2][1] = 0.5 * dv[4]; dS.m[2][2] = dv[5];
+    const double dB[3] = {dv[6], dv[7], dv[8]};
+    const double dC = dv[9];
 
     // dL_dS_inv_square_R = R_transpose * dL_dSigma + outerProduct(t2, dL_dB)   (backward.cu:458)
     M3 dSR = m3_mul(Rt, dS);
@@ -287,21 +304,21 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) dRt.m[c][rr] += (float)(si[rr] * dSR.m[c][rr]);
+      for (int rr = 0; rr < 3; ++rr) dRt.m[c][rr] += si[rr] * dSR.m[c][rr];
     // :471-484
-    float dSi[3], dt2[3];
+    double dSi[3], dt2[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       dSi[i] = dSR.m[0][i] * Rt.m[0][i] + dSR.m[1][i] * Rt.m[1][i] + dSR.m[2][i] * Rt.m[2][i];
-      dt2[i] = (float)(2 * t2[i] * si[i] * dC + dB[0] * SR.m[0][i] + dB[1] * SR.m[1][i] + dB[2] * SR.m[2][i]);
+      dt2[i] = 2 * t2[i] * si[i] * dC + dB[0] * SR.m[0][i] + dB[1] * SR.m[1][i] + dB[2] * SR.m[2][i];
       dSi[i] += dC * t2[i] * t2[i];
     }
-    const float sc[3] = {sx, sy, sz};
+    const double sc[3] = {sx, sy, sz};
 #pragma unroll
     for (int i = 0; i < 3; ++i) a.dL_dscale[3 * idx + i] = (float)(-2 / sc[i] * si[i] * dSi[i]);   // :486-497
 
     // :523-535  dL_dG2V_R[c][r] = dL_dRt[r][c] - dt2[c]*t[r];  dL_dG2V_t[c] = sum_r (-dt2[r]) * Rt[c][r]
-    float dG2V[4][3];
+    double dG2V[4][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -310,24 +327,24 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
     for (int c = 0; c < 3; ++c)
       dG2V[3][c] = Rt.m[c][0] * (-dt2[0]) + Rt.m[c][1] * (-dt2[1]) + Rt.m[c][2] * (-dt2[2]);
     // dL_dG2W = transpose(W2V) * dL_dG2V  (:547): [c][r] = sum_k vm[4r+k] * dG2V[c][k], k<3 (4th row is 0)
-    float dG2W[4][3];
+    double dG2W[4][3];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr)
         dG2W[c][rr] = vm[4 * rr + 0] * dG2V[c][0] + vm[4 * rr + 1] * dG2V[c][1] + vm[4 * rr + 2] * dG2V[c][2];
-    dmean[0] = dG2W[3][0]; dmean[1] = dG2W[3][1]; dmean[2] = dG2W[3][2];   // :570-573
+    dmean[0] = (float)dG2W[3][0]; dmean[1] = (float)dG2W[3][1]; dmean[2] = (float)dG2W[3][2];   // :570-573
 
     // :575-586 quaternion gradient from dL_dMt = dL_dG2W_R
 #define MT(c, r) dG2W[c][r]
     float4 dq;
-    dq.x = 2 * z * (MT(0, 1) - MT(1, 0)) + 2 * y * (MT(2, 0) - MT(0, 2)) + 2 * x * (MT(1, 2) - MT(2, 1));
-    dq.y = 2 * y * (MT(1, 0) + MT(0, 1)) + 2 * z * (MT(2, 0) + MT(0, 2)) + 2 * r * (MT(1, 2) - MT(2, 1)) -
-           4 * x * (MT(2, 2) + MT(1, 1));
-    dq.z = 2 * x * (MT(1, 0) + MT(0, 1)) + 2 * r * (MT(2, 0) - MT(0, 2)) + 2 * z * (MT(1, 2) + MT(2, 1)) -
-           4 * y * (MT(2, 2) + MT(0, 0));
-    dq.w = 2 * r * (MT(0, 1) - MT(1, 0)) + 2 * x * (MT(2, 0) + MT(0, 2)) + 2 * y * (MT(1, 2) + MT(2, 1)) -
-           4 * z * (MT(1, 1) + MT(0, 0));
+    dq.x = (float)(2 * z * (MT(0, 1) - MT(1, 0)) + 2 * y * (MT(2, 0) - MT(0, 2)) + 2 * x * (MT(1, 2) - MT(2, 1)));
+    dq.y = (float)(2 * y * (MT(1, 0) + MT(0, 1)) + 2 * z * (MT(2, 0) + MT(0, 2)) + 2 * r * (MT(1, 2) - MT(2, 1)) -
+                   4 * x * (MT(2, 2) + MT(1, 1)));
+    dq.z = (float)(2 * x * (MT(1, 0) + MT(0, 1)) + 2 * r * (MT(2, 0) - MT(0, 2)) + 2 * z * (MT(1, 2) + MT(2, 1)) -
+                   4 * y * (MT(2, 2) + MT(0, 0)));
+    dq.w = (float)(2 * r * (MT(0, 1) - MT(1, 0)) + 2 * x * (MT(2, 0) + MT(0, 2)) + 2 * y * (MT(1, 2) + MT(2, 1)) -
+                   4 * z * (MT(1, 1) + MT(0, 0)));
 #undef MT
     reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
   }
@@ -440,6 +457,12 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
   a.clamped = reinterpret_cast<unsigned char*>(geom + L.clamped);
   a.depth_key = reinterpret_cast<uint32_t*>(geom + L.key_a);
   a.order = reinterpret_cast<uint32_t*>(geom + L.val_a);
+  a.depth = reinterpret_cast<float*>(geom + L.depth);
+  {
+    static int cull = -1;   // GOF_CULL=0 disables the alpha-support boxes (A/B testing; results are identical)
+    if (cull < 0) { const char* e = getenv("GOF_CULL"); cull = (e && e[0] == '0') ? 0 : 1; }
+    a.cull = cull;
+  }
   GOF_LAUNCH("preprocess_fwd", st, k_preprocess<<<(s->P + 255) / 256, 256, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;

@@ -1,11 +1,12 @@
 // render_bwd.cu -- K7: per-tile back-to-front gradient pass (backward.cu:634-955).
 //
 // The reference issues 17 global float atomics per contributing (pixel,Gaussian) pair
-// (backward.cu:836,905-912,943-952).  Here the 17 partial gradients are first summed over the warp with
-// shuffles, accumulated per (tile,Gaussian) in shared memory, and flushed with at most 17 global atomics
-// per (tile,Gaussian) instance.  Pairs are re-evaluated with exactly the forward's operation sequence
-// (gof_math.cuh) so that the recomputed alpha equals the forward's; the traversal starts at the last
-// Gaussian any pixel of the tile actually blended instead of at the end of the tile list.
+// (backward.cu:836,905-912,943-952).  Here a warp owns an 8x4 pixel block; the partial gradients of its 32
+// pixels are summed with a 16-shuffle butterfly (dL_dopacity is -2/opacity * dL_dC, so 16 values carry all
+// 17 outputs) and leave the SM as at most 17 atomics per (warp,Gaussian).  Pairs are re-evaluated with exactly
+// the forward's operation sequence (gof_math.cuh) so that the recomputed alpha equals the forward's; the
+// traversal starts at the last Gaussian any pixel of the tile actually blended, warps skip Gaussians behind
+// their own deepest contributor and Gaussians whose alpha-support box (gof_cull_bbox) misses their pixels.
 #include "gof_common.cuh"
 #include "gof_math.cuh"
 
@@ -27,30 +28,61 @@ struct BwdArgs {
   float* dL_dopacity;  // [P]
   float* dL_dcolor;    // [P,3]
   float* dL_dv2g;      // [P,10]
+  unsigned long long* stats;   // optional [8] counters (GOF_STATS=1), else nullptr
 };
 
 constexpr int BATCH = GOF_BLOCK_SIZE;
-constexpr int NGRAD = 17;   // 3 colour + 3 mean2D + 1 opacity + 10 view2gaussian
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
+__device__ __forceinline__ bool box_hits(uint32_t lo, uint32_t hi, int wx0, int wy0, int wx1, int wy1) {
+  const int x0 = (int)(short)(lo & 0xffffu), y0 = (int)(short)(lo >> 16);
+  const int x1 = (int)(short)(hi & 0xffffu), y1 = (int)(short)(hi >> 16);
+  return x0 <= wx1 && x1 >= wx0 && y0 <= wy1 && y1 >= wy0;
 }
 
-__global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_backward(const BwdArgs a) {
+// Sum 16 per-lane values over the warp with 16 shuffles (instead of 16 x 5): at every step each lane keeps half of
+// its values and trades the other half with its partner.  On return `r` holds, in BOTH lanes of each even/odd
+// pair, the warp-wide sum of value number (lane >> 1).
+__device__ __forceinline__ float warp_reduce16(const float (&a)[16], int lane) {
+  float b[8], c[4], d[2], e;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = h16 ? a[i] : a[i + 8], keep = h16 ? a[i + 8] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h8 ? b[i] : b[i + 4], keep = h8 ? b[i + 4] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h4 ? c[i] : c[i + 2], keep = h4 ? c[i + 2] : c[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = h2 ? d[0] : d[1], keep = h2 ? d[1] : d[0];
+    e = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  e += __shfl_xor_sync(0xffffffffu, e, 1);
+  return e;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(GOF_BLOCK_SIZE, 3) k_render_backward(const BwdArgs a) {
+  unsigned long long st_visit = 0, st_eval = 0, st_pass = 0, st_contrib = 0, st_anyhit = 0;
   __shared__ float4 s_rec[BATCH][4];
   __shared__ float4 s_recb[BATCH][2];
   __shared__ float s_thr[BATCH];
   __shared__ uint32_t s_id[BATCH];
-  __shared__ float s_grad[NGRAD][BATCH];
   __shared__ uint32_t s_max;
 
   const int tile = blockIdx.x;
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t pix_x = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-  const uint32_t pix_y = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+  const int wx0 = tile_x * 16 + (warp & 1) * 8, wy0 = tile_y * 16 + (warp >> 1) * 4;
+  const uint32_t pix_x = wx0 + (lane & 7);
+  const uint32_t pix_y = wy0 + (lane >> 3);
   const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
   const float rx = gof_ray(pix_x, a.W, a.focal_x);
   const float ry = gof_ray(pix_y, a.H, a.focal_y);
@@ -76,15 +108,14 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_backward(const BwdArg
   }
   const float bg_dot_dpixel = a.bg[0] * dpix0 + a.bg[1] * dpix1 + a.bg[2] * dpix2;
 
-  // traversal starts at the deepest Gaussian any pixel of this tile blended
+  // traversal starts at the deepest Gaussian any pixel of this tile blended; each warp additionally skips
+  // everything behind the deepest Gaussian ITS 32 pixels blended
+  uint32_t warp_last = last_contributor;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, d));
   if (threadIdx.x == 0) s_max = 0u;
   __syncthreads();
-  {
-    uint32_t m = last_contributor;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if (lane == 0) atomicMax(&s_max, m);
-  }
+  if (lane == 0) atomicMax(&s_max, warp_last);
   __syncthreads();
   const int used = (int)min(s_max, range.y - range.x);
   const int rounds = (used + BATCH - 1) / BATCH;
@@ -93,6 +124,13 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_backward(const BwdArg
   float last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f, acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
   float last_n0 = 0.f, last_n1 = 0.f, last_n2 = 0.f, acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f;
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+
+  // which output the even lanes of the butterfly feed: value index v = lane >> 1
+  //   v 0..9 -> dL_dview2gaussian[0..9] (v 9 = dL_dC also yields dL_dopacity = -2/opacity * that sum: both are
+  //   G*dL_dalpha up to a per-Gaussian constant; dL_dC is the one carried through the reduction because the
+  //   view2gaussian chain rule cancels it against the other nine to ~1e-5 and needs them rounded consistently),
+  //   v 10..12 -> dL_dcolor, v 13..15 -> dL_dmean2D
+  const int vidx = lane >> 1;
 
   int toDo = used;
   for (int i = 0; i < rounds; ++i, toDo -= BATCH) {
@@ -110,150 +148,147 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_backward(const BwdArg
       const float op = r2.z;
       s_thr[threadIdx.x] = (op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
     }
-#pragma unroll
-    for (int k = 0; k < NGRAD; ++k) s_grad[k][threadIdx.x] = 0.f;
     __syncthreads();
 
     const int nb = toDo < BATCH ? toDo : BATCH;
-    for (int j = 0; j < nb; ++j) {
-      // zero-based index of this Gaussian in the tile list == the reference's `contributor` after its
-      // decrement (backward.cu:763)
-      const uint32_t contributor = (uint32_t)(used - 1 - (i * BATCH + j));
-      bool contrib = inside && contributor < last_contributor;
+    // Sub-batches of 32: ballot the Gaussians that can reach this warp's 8x4 pixels AND lie in front of its deepest
+    // contributor, then visit only those (loop NOT unrolled: one copy of the ~10 KB body, see render_fwd.cu)
+#pragma unroll 1
+    for (int k = 0; k < BATCH / 32; ++k) {
+      if (k * 32 >= nb) break;
+      const int idx = k * 32 + lane;
+      const float4 qb = s_rec[idx][3];
+      const uint32_t cidx = (uint32_t)(used - 1 - (i * BATCH + idx));
+      uint32_t m = __ballot_sync(0xffffffffu, idx < nb && cidx < warp_last &&
+                                                  box_hits(__float_as_uint(qb.z), __float_as_uint(qb.w), wx0, wy0, wx0 + 7, wy0 + 3));
+      while (m) {
+        const int j = k * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        // zero-based index of this Gaussian in the tile list == the reference's `contributor` after its
+        // decrement (backward.cu:763)
+        const uint32_t contributor = (uint32_t)(used - 1 - (i * BATCH + j));
+        bool contrib = inside && contributor < last_contributor;
+        if (STATS) { st_visit += (lane == 0); st_eval += contrib; }
 
-      const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
-      const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-      GofPair p;
-      float t = 0.f, G = 0.f, alpha = 0.f;
-      if (contrib) {
-        p = gof_pair_geom(v, rx, ry);
-        const float bh = 0.5f * p.BB;
-        const float qf = bh * bh * __frcp_rn(p.AA);
-        const float pw = -0.5f * (v[9] - qf);
-        const float bound = fmaf(fabsf(qf), 3e-7f, pw);
-        if (bound < s_thr[j] && fabsf(p.AA) < 1e30f) contrib = false;
-      }
-      if (contrib) {
-        t = gof_pair_t(p);
-        if ((double)t <= GOF_NEAR_PLANE_D) contrib = false;
-      }
-      if (contrib) {
-        const float power = gof_pair_power(p, v[9]);
-        G = F_EXP(power);
-        alpha = fminf(F_MUL(q2.z, G), GOF_ALPHA_MAX);
-        if (alpha < GOF_ALPHA_MIN) contrib = false;
-      }
-      if (!__any_sync(0xffffffffu, contrib)) continue;
+        const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
+        const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+        GofPair p;
+        float t = 0.f, G = 0.f, alpha = 0.f;
+        double qd = 0.0;
+        if (contrib) {
+          p = gof_pair_geom(v, rx, ry);
+          const float bh = 0.5f * p.BB;
+          const float qf = bh * bh * __frcp_rn(p.AA);
+          const float pw = -0.5f * (v[9] - qf);
+          const float bound = fmaf(fabsf(qf), 3e-7f, pw);
+          if (bound < s_thr[j] && fabsf(p.AA) < 1e30f) contrib = false;
+        }
+        if (STATS) st_pass += contrib;
+        if (contrib) {
+          float power;
+          gof_pair_t_power(p, v[9], &t, &power, &qd);
+          if ((double)t <= GOF_NEAR_PLANE_D) contrib = false;
+          else {
+            G = F_EXP(power);
+            alpha = fminf(F_MUL(q2.z, G), GOF_ALPHA_MAX);
+            if (alpha < GOF_ALPHA_MIN) contrib = false;
+          }
+        }
+        if (STATS) st_contrib += contrib;
+        if (!__any_sync(0xffffffffu, contrib)) continue;
+        if (STATS) st_anyhit += (lane == 0);
 
-      float g[NGRAD];
+        float g[16];
 #pragma unroll
-      for (int k = 0; k < NGRAD; ++k) g[k] = 0.f;
-      if (contrib) {
-        // backward.cu:806-817
-        const double td = (double)t;
-        const float m = gof_mapped_t(t);
-        const float dm_dt = (float)(20.0 / ((99.8 * td) * td));
-        const float len = gof_normal_length(p);
-        const float nn0 = -p.n0 / len, nn1 = -p.n1 / len, nn2 = -p.n2 / len;
-        T = T / (1.f - alpha);
-        const float w = alpha * T;
-        float dL_dalpha = 0.f;
-        // colour, :824-837
-        const float4 q3 = s_rec[j][3];
-        const float c0 = q2.w, c1 = q3.x, c2 = q3.y;
-        acc_c0 = last_alpha * last_c0 + (1.f - last_alpha) * acc_c0; last_c0 = c0;
-        acc_c1 = last_alpha * last_c1 + (1.f - last_alpha) * acc_c1; last_c1 = c1;
-        acc_c2 = last_alpha * last_c2 + (1.f - last_alpha) * acc_c2; last_c2 = c2;
-        dL_dalpha += (c0 - acc_c0) * dpix0;
-        dL_dalpha += (c1 - acc_c1) * dpix1;
-        dL_dalpha += (c2 - acc_c2) * dpix2;
-        g[0] = w * dpix0; g[1] = w * dpix1; g[2] = w * dpix2;
-        // distortion: only the depth path survives ("detach weight", :848-858)
-        const float dL_dmax_t = 2.0f * (T * alpha) * (m * final_A - final_D) * dreg * dm_dt;
-        // normal, :860-877
-        acc_n0 = last_alpha * last_n0 + (1.f - last_alpha) * acc_n0; last_n0 = nn0;
-        acc_n1 = last_alpha * last_n1 + (1.f - last_alpha) * acc_n1; last_n1 = nn1;
-        acc_n2 = last_alpha * last_n2 + (1.f - last_alpha) * acc_n2; last_n2 = nn2;
-        dL_dalpha += (nn0 - acc_n0) * dn0;
-        dL_dalpha += (nn1 - acc_n1) * dn1;
-        dL_dalpha += (nn2 - acc_n2) * dn2;
-        const float dnn0 = w * dn0, dnn1 = w * dn1, dnn2 = w * dn2;
-        float dL_dlength = dnn0 * p.n0 + dnn1 * p.n1 + dnn2 * p.n2;
-        dL_dlength *= 1.f / (len * len);
-        float dnrm0 = (-dnn0 + dL_dlength * p.n0) / len;
-        float dnrm1 = (-dnn1 + dL_dlength * p.n1) / len;
-        float dnrm2 = (-dnn2 + dL_dlength * p.n2) / len;
-        // :879-893
-        float dL_dt = dL_dmax_t;
-        if (contributor == max_contributor - 1u) dL_dt += ddepth;
-        dL_dalpha *= T;
-        last_alpha = alpha;
-        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-        // :896-912  2D-mean statistic and opacity
-        const float4 b0 = s_recb[j][0], b1 = s_recb[j][1];   // (mx,my,cx,cy) (cz,..)
-        const float dx = b0.x - (float)pix_x, dy = b0.y - (float)pix_y;
-        const float dL_dG = q2.z * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * b0.z - gdy * b0.w;
-        const float dG_ddely = -gdy * b1.x - gdx * b0.w;
-        g[3] = dL_dG * dG_ddelx * ddelx_dx;
-        g[4] = dL_dG * dG_ddely * ddely_dy;
-        g[5] = fabsf(g[3]) + fabsf(g[4]);
-        g[6] = G * dL_dalpha;
-        // :914-928
-        const float dL_dpower = dL_dG * G;
-        const float dL_dmin = dL_dpower * -0.5f;
-        const double AA = (double)p.AA, BB = (double)p.BB;
-        const double boa = BB / AA;
-        double dL_dA = (double)dL_dmin * boa * boa / 4.0;
-        double dL_dB = (double)dL_dmin * -BB / (2 * AA);
-        const float dL_dC = dL_dmin;
-        dL_dA += (double)dL_dt * BB / (2 * AA * AA);
-        dL_dB += (double)dL_dt * -1.0 / (2 * AA);
-        // :938-952
-        dnrm0 = (float)(dnrm0 + dL_dA * rx);
-        dnrm1 = (float)(dnrm1 + dL_dA * ry);
-        dnrm2 = (float)(dnrm2 + dL_dA);
-        g[7] = dnrm0 * rx;
-        g[8] = dnrm0 * ry + dnrm1 * rx;
-        g[9] = dnrm0 + dnrm2 * rx;
-        g[10] = dnrm1 * ry;
-        g[11] = dnrm1 + dnrm2 * ry;
-        g[12] = dnrm2;
-        g[13] = (float)(dL_dB * 2 * rx);
-        g[14] = (float)(dL_dB * 2 * ry);
-        g[15] = (float)(dL_dB * 2);
-        g[16] = dL_dC;
-      }
-#pragma unroll
-      for (int k = 0; k < NGRAD; ++k) {
-        const float s = warp_sum(g[k]);
-        if (lane == k) atomicAdd(&s_grad[k][j], s);
+        for (int q = 0; q < 16; ++q) g[q] = 0.f;
+        if (contrib) {
+          // backward.cu:806-817
+          const float mt = gof_mapped_t(t);
+          const float dm_dt = 20.0f / ((99.8f * t) * t);
+          const float len = gof_normal_length(p);
+          const float rlen = 1.0f / len;
+          const float nn0 = -p.n0 * rlen, nn1 = -p.n1 * rlen, nn2 = -p.n2 * rlen;
+          T = T / (1.f - alpha);
+          const float w = alpha * T;
+          float dL_dalpha = 0.f;
+          // colour, :824-837
+          const float4 q3 = s_rec[j][3];
+          const float c0 = q2.w, c1 = q3.x, c2 = q3.y;
+          acc_c0 = last_alpha * last_c0 + (1.f - last_alpha) * acc_c0; last_c0 = c0;
+          acc_c1 = last_alpha * last_c1 + (1.f - last_alpha) * acc_c1; last_c1 = c1;
+          acc_c2 = last_alpha * last_c2 + (1.f - last_alpha) * acc_c2; last_c2 = c2;
+          dL_dalpha += (c0 - acc_c0) * dpix0;
+          dL_dalpha += (c1 - acc_c1) * dpix1;
+          dL_dalpha += (c2 - acc_c2) * dpix2;
+          g[10] = w * dpix0; g[11] = w * dpix1; g[12] = w * dpix2;
+          // distortion: only the depth path survives ("detach weight", :848-858)
+          const float dL_dmax_t = 2.0f * (T * alpha) * (mt * final_A - final_D) * dreg * dm_dt;
+          // normal, :860-877
+          acc_n0 = last_alpha * last_n0 + (1.f - last_alpha) * acc_n0; last_n0 = nn0;
+          acc_n1 = last_alpha * last_n1 + (1.f - last_alpha) * acc_n1; last_n1 = nn1;
+          acc_n2 = last_alpha * last_n2 + (1.f - last_alpha) * acc_n2; last_n2 = nn2;
+          dL_dalpha += (nn0 - acc_n0) * dn0;
+          dL_dalpha += (nn1 - acc_n1) * dn1;
+          dL_dalpha += (nn2 - acc_n2) * dn2;
+          const float dnn0 = w * dn0, dnn1 = w * dn1, dnn2 = w * dn2;
+          const float dL_dlength = (dnn0 * p.n0 + dnn1 * p.n1 + dnn2 * p.n2) * (rlen * rlen);
+          float dnrm0 = (-dnn0 + dL_dlength * p.n0) * rlen;
+          float dnrm1 = (-dnn1 + dL_dlength * p.n1) * rlen;
+          float dnrm2 = (-dnn2 + dL_dlength * p.n2) * rlen;
+          // :879-893
+          float dL_dt = dL_dmax_t;
+          if (contributor == max_contributor - 1u) dL_dt += ddepth;
+          dL_dalpha *= T;
+          last_alpha = alpha;
+          dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+          // :896-912  2D-mean statistic and opacity
+          const float4 b0 = s_recb[j][0], b1 = s_recb[j][1];   // (mx,my,cx,cy) (cz,..)
+          const float dx = b0.x - (float)pix_x, dy = b0.y - (float)pix_y;
+          const float dL_dG = q2.z * dL_dalpha;
+          const float gdx = G * dx, gdy = G * dy;
+          const float dG_ddelx = -gdx * b0.z - gdy * b0.w;
+          const float dG_ddely = -gdy * b1.x - gdx * b0.w;
+          g[13] = dL_dG * dG_ddelx * ddelx_dx;
+          g[14] = dL_dG * dG_ddely * ddely_dy;
+          g[15] = fabsf(g[13]) + fabsf(g[14]);
+          // :914-928 in double like the reference; BB/AA = -qd is reused from the forward evaluation
+          const float dL_dmin = dL_dG * G * -0.5f;
+          g[9] = dL_dmin;   // dL_dC; dL_dopacity = G*dL_dalpha = dL_dC * (-2/opacity) is derived from its sum below
+          const double inv2A = 0.5 / (double)p.AA;
+          const double dL_dA = (double)dL_dmin * qd * qd * 0.25 - (double)dL_dt * qd * inv2A;
+          const double dL_dB = (double)dL_dmin * qd * 0.5 - (double)dL_dt * inv2A;
+          // :938-952
+          dnrm0 = (float)((double)dnrm0 + dL_dA * rx);
+          dnrm1 = (float)((double)dnrm1 + dL_dA * ry);
+          dnrm2 = (float)((double)dnrm2 + dL_dA);
+          g[0] = dnrm0 * rx;
+          g[1] = dnrm0 * ry + dnrm1 * rx;
+          g[2] = dnrm0 + dnrm2 * rx;
+          g[3] = dnrm1 * ry;
+          g[4] = dnrm1 + dnrm2 * ry;
+          g[5] = dnrm2;
+          g[6] = (float)(dL_dB * 2.0 * rx);
+          g[7] = (float)(dL_dB * 2.0 * ry);
+          g[8] = (float)(dL_dB * 2.0);
+        }
+        const float sum = warp_reduce16(g, lane);
+        // one red per even lane: 17 global float atomics per (warp, Gaussian) instead of per (pixel, Gaussian)
+        const uint32_t gid = s_id[j];
+        if (!(lane & 1) && sum != 0.f) {
+          float* dst;
+          if (vidx < 10) dst = a.dL_dv2g + 10 * (size_t)gid + vidx;
+          else if (vidx < 13) dst = a.dL_dcolor + 3 * (size_t)gid + (vidx - 10);
+          else dst = a.dL_dmean2D + 3 * (size_t)gid + (vidx - 13);
+          atomicAdd(dst, sum);
+          if (vidx == 9) atomicAdd(a.dL_dopacity + gid, sum * (-2.0f / q2.z));   // alpha >= 1/255 implies opacity > 0
+        }
       }
     }
-    __syncthreads();
-    // flush this batch: thread j owns Gaussian j of the batch
-    if ((int)threadIdx.x < nb) {
-      const uint32_t gid = s_id[threadIdx.x];
-      float g[NGRAD];
-      bool any = false;
-#pragma unroll
-      for (int k = 0; k < NGRAD; ++k) {
-        g[k] = s_grad[k][threadIdx.x];
-        any |= (g[k] != 0.f);
-      }
-      if (any) {
-        atomicAdd(a.dL_dcolor + 3 * (size_t)gid + 0, g[0]);
-        atomicAdd(a.dL_dcolor + 3 * (size_t)gid + 1, g[1]);
-        atomicAdd(a.dL_dcolor + 3 * (size_t)gid + 2, g[2]);
-        atomicAdd(a.dL_dmean2D + 3 * (size_t)gid + 0, g[3]);
-        atomicAdd(a.dL_dmean2D + 3 * (size_t)gid + 1, g[4]);
-        atomicAdd(a.dL_dmean2D + 3 * (size_t)gid + 2, g[5]);
-        atomicAdd(a.dL_dopacity + gid, g[6]);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) atomicAdd(a.dL_dv2g + 10 * (size_t)gid + k, g[7 + k]);
-      }
-    }
+  }
+  if (STATS && a.stats) {
+    atomicAdd(a.stats + 0, st_visit); atomicAdd(a.stats + 1, st_eval); atomicAdd(a.stats + 2, st_pass);
+    atomicAdd(a.stats + 3, st_contrib); atomicAdd(a.stats + 4, st_anyhit);
+    if (threadIdx.x == 0) { atomicAdd(a.stats + 5, (unsigned long long)used); atomicAdd(a.stats + 6, (unsigned long long)(range.y - range.x)); }
   }
 }
 
@@ -275,7 +310,9 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, const cha
   a.dL_dpix = dL_dpix;
   a.plane = (size_t)v.tiles * 256;
   a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g;
-  GOF_LAUNCH("render_bwd", st, k_render_backward<<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  a.stats = gof_stats_buffer();
+  if (a.stats) GOF_LAUNCH("render_bwd", st, k_render_backward<true><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  else GOF_LAUNCH("render_bwd", st, k_render_backward<false><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }

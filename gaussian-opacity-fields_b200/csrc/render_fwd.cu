@@ -4,6 +4,9 @@
 //  * a warp covers an 8x4 pixel block (not a 16x2 strip) so the 32 rays of a warp are spatially compact;
 //  * each (tile,Gaussian) instance is gathered as ONE 64-byte record (two sectors) and the gather for batch
 //    i+1 is issued before batch i is blended (register double buffering);
+//  * every record carries a conservative pixel box of the region where its alpha can reach 1/255
+//    (gof_cull_bbox); each warp ballots the 256 staged boxes against its own 8x4 pixel block and only visits
+//    the Gaussians that can touch it;
 //  * a conservative single-precision pre-test discards pairs whose alpha is provably < 1/255 before the
 //    reference's double-precision evaluation; every pair that survives is evaluated with exactly the
 //    reference's operation sequence (gof_math.cuh), so accepted alphas are bit-identical.
@@ -27,15 +30,22 @@ struct FwdArgs {
 
 constexpr int BATCH = GOF_BLOCK_SIZE;
 
+__device__ __forceinline__ bool box_hits(uint32_t lo, uint32_t hi, int wx0, int wy0, int wx1, int wy1) {
+  const int x0 = (int)(short)(lo & 0xffffu), y0 = (int)(short)(lo >> 16);
+  const int x1 = (int)(short)(hi & 0xffffu), y1 = (int)(short)(hi >> 16);
+  return x0 <= wx1 && x1 >= wx0 && y0 <= wy1 && y1 >= wy0;
+}
+
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs a) {
   __shared__ float4 s_rec[BATCH][4];   // 16 KB: the 64-byte records of the current batch
-  __shared__ float s_thr[BATCH];       // ln(1/(255*opacity)) - the largest power that can still be rejected
+  __shared__ float s_thr[BATCH];       // -ln(255*opacity): the largest power that can still be rejected
 
   const int tile = blockIdx.x;
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t pix_x = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-  const uint32_t pix_y = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+  const int wx0 = tile_x * 16 + (warp & 1) * 8, wy0 = tile_y * 16 + (warp >> 1) * 4;   // this warp's 8x4 pixel block
+  const uint32_t pix_x = wx0 + (lane & 7);
+  const uint32_t pix_y = wy0 + (lane >> 3);
   const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
   bool done = !inside;
 
@@ -47,7 +57,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs
   const int rounds = (total + BATCH - 1) / BATCH;
 
   float T = 1.0f;
-  uint32_t contributor = 0, last_contributor = 0, max_contributor = 0xFFFFFFFFu;
+  uint32_t last_contributor = 0, max_contributor = 0xFFFFFFFFu;
   float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, Dm = 0.f, Aacc = 0.f;
   float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
 
@@ -67,9 +77,9 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs
     s_rec[threadIdx.x][0] = nx0; s_rec[threadIdx.x][1] = nx1;
     s_rec[threadIdx.x][2] = nx2; s_rec[threadIdx.x][3] = nx3;
     {
-      const float op = nx2.z;   // v2g[8], v2g[9], opacity, rgb0
+      const float op = nx2.z;   // (v2g[8], v2g[9], opacity, rgb0)
       // alpha = op*exp(power) < 1/255  <=>  power < -ln(255*op);   op <= 0 can never contribute
-      s_thr[threadIdx.x] = (op > 0.f) ? (-__logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
+      s_thr[threadIdx.x] = (op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
     }
     __syncthreads();
     // issue the gather for the next batch; it completes while this batch is blended
@@ -83,56 +93,71 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs
     }
 
     const int nb = toDo < BATCH ? toDo : BATCH;
-    for (int j = 0; !done && j < nb; ++j) {
-      contributor++;
-      const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
-      const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-      const GofPair p = gof_pair_geom(v, rx, ry);
+    if (__all_sync(0xffffffffu, done)) continue;   // this warp's 32 pixels are saturated (it still helps staging)
 
-      // ---- conservative reject (single precision, error-bounded) ----
-      {
-        const float bh = 0.5f * p.BB;
-        const float qf = bh * bh * __frcp_rn(p.AA);           // ~ BB^2/(4AA), rel. error < 3e-7
-        const float pw = -0.5f * (v[9] - qf);                  // approximate power
-        const float bound = fmaf(fabsf(qf), 3e-7f, pw);        // pw + |error|
-        if (bound < s_thr[j] && fabsf(p.AA) < 1e30f) continue;
-      }
+    // Sub-batches of 32: ballot which of these 32 staged Gaussians can reach this warp's 8x4 pixels at all, then
+    // visit only those.  (The loop is deliberately NOT unrolled: the body is ~10 KB of SASS and eight copies
+    // of it thrash the instruction cache -- ncu: 65 % of stall samples were "no instruction".)
+#pragma unroll 1
+    for (int k = 0; k < BATCH / 32; ++k) {
+      if (k * 32 >= nb) break;
+      const int idx = k * 32 + lane;
+      const float4 qb = s_rec[idx][3];
+      uint32_t m = __ballot_sync(0xffffffffu, idx < nb && box_hits(__float_as_uint(qb.z), __float_as_uint(qb.w), wx0, wy0, wx0 + 7, wy0 + 3));
+      while (m) {
+        const int j = k * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        if (done) continue;
+        const uint32_t contributor = (uint32_t)(i * BATCH + j + 1);   // 1-based position in the tile list
+        const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
+        const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+        const GofPair p = gof_pair_geom(v, rx, ry);
 
-      // ---- exact path: forward.cu:516-541 ----
-      const float t = gof_pair_t(p);
-      if ((double)t <= GOF_NEAR_PLANE_D) continue;
-      const float power = gof_pair_power(p, v[9]);
-      const float alpha = fminf(F_MUL(q2.z, F_EXP(power)), GOF_ALPHA_MAX);
-      if (alpha < GOF_ALPHA_MIN) continue;
-      const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
-      if (test_T < GOF_T_EPS) {
-        done = true;
-        continue;
+        // ---- conservative reject (single precision, error-bounded) ----
+        {
+          const float bh = 0.5f * p.BB;
+          const float qf = bh * bh * __frcp_rn(p.AA);           // ~ BB^2/(4AA), rel. error < 3e-7
+          const float pw = -0.5f * (v[9] - qf);                  // approximate power
+          const float bound = fmaf(fabsf(qf), 3e-7f, pw);        // pw + |error|
+          if (bound < s_thr[j] && fabsf(p.AA) < 1e30f) continue;
+        }
+
+        // ---- exact path: forward.cu:516-541 ----
+        float t, power;
+        gof_pair_t_power(p, v[9], &t, &power);
+        if ((double)t <= GOF_NEAR_PLANE_D) continue;
+        const float alpha = fminf(F_MUL(q2.z, F_EXP(power)), GOF_ALPHA_MAX);
+        if (alpha < GOF_ALPHA_MIN) continue;
+        const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
+        if (test_T < GOF_T_EPS) {
+          done = true;
+          continue;
+        }
+        // forward.cu:543-578 (accumulation order = the reference's SASS: fma onto T)
+        const float mt = gof_mapped_t(t);
+        const float len = gof_normal_length(p);
+        const float nn0 = F_DIV(p.n0, len), nn1 = F_DIV(p.n1, len), nn2 = F_DIV(p.n2, len);
+        const float A = F_SUB(1.0f, T);
+        const float m2 = F_MUL(mt, mt);
+        const float err = F_FMA(-dist1, F_ADD(mt, mt), F_FMA(A, m2, dist2));
+        distortion = F_FMA(T, F_MUL(err, alpha), distortion);
+        dist1 = F_FMA(T, F_MUL(alpha, mt), dist1);
+        dist2 = F_FMA(T, F_MUL(m2, alpha), dist2);
+        const float4 q3 = s_rec[j][3];
+        C0 = F_FMA(T, F_MUL(alpha, q2.w), C0);
+        C1 = F_FMA(T, F_MUL(alpha, q3.x), C1);
+        C2 = F_FMA(T, F_MUL(alpha, q3.y), C2);
+        N0 = F_FMA(-T, F_MUL(alpha, nn0), N0);
+        N1 = F_FMA(-T, F_MUL(alpha, nn1), N1);
+        N2 = F_FMA(-T, F_MUL(alpha, nn2), N2);
+        if (T > 0.5f) {
+          Dm = t;
+          max_contributor = contributor;
+        }
+        Aacc = F_FMA(T, alpha, Aacc);
+        T = test_T;
+        last_contributor = contributor;
       }
-      // forward.cu:543-578
-      const float m = gof_mapped_t(t);
-      const float len = gof_normal_length(p);
-      const float nn0 = F_DIV(p.n0, len), nn1 = F_DIV(p.n1, len), nn2 = F_DIV(p.n2, len);
-      const float A = F_SUB(1.0f, T);
-      const float m2 = F_MUL(m, m);
-      const float err = F_FMA(-dist1, F_ADD(m, m), F_FMA(A, m2, dist2));
-      distortion = F_FMA(T, F_MUL(err, alpha), distortion);
-      dist1 = F_FMA(T, F_MUL(alpha, m), dist1);
-      dist2 = F_FMA(T, F_MUL(m2, alpha), dist2);
-      const float4 q3 = s_rec[j][3];
-      C0 = F_FMA(T, F_MUL(alpha, q2.w), C0);
-      C1 = F_FMA(T, F_MUL(alpha, q3.x), C1);
-      C2 = F_FMA(T, F_MUL(alpha, q3.y), C2);
-      N0 = F_FMA(-T, F_MUL(alpha, nn0), N0);
-      N1 = F_FMA(-T, F_MUL(alpha, nn1), N1);
-      N2 = F_FMA(-T, F_MUL(alpha, nn2), N2);
-      if (T > 0.5f) {
-        Dm = t;
-        max_contributor = contributor;
-      }
-      Aacc = F_FMA(T, alpha, Aacc);
-      T = test_T;
-      last_contributor = contributor;
     }
   }
 

@@ -742,3 +742,26 @@ void oracle_mark_visible(int P, const float* means3D, const float* vm, unsigned 
     present[i] = !(z <= 0.2f);
   }
 }
+
+/* Test helper: the reference's per-pixel alpha of ONE Gaussian over the whole image (0 where the pair is rejected by
+ * t <= 0.2 or alpha < 1/255), forward.cu:499-535.  Used to check conservative culling bounds. */
+void oracle_alpha_map(int W, int H, float tan_fovx, float tan_fovy, const float* v2g, float opacity, float* out) {
+  const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
+  for (int py = 0; py < H; ++py)
+    for (int px = 0; px < W; ++px) {
+      const float pixfx = (float)px + 0.5f, pixfy = (float)py + 0.5f;
+      const float rx = (float)((pixfx - W / 2.) / focal_x), ry = (float)((pixfy - H / 2.) / focal_y);
+      const pair_t p = pair_geom(v2g, rx, ry);
+      const double AA = p.AA, BB = p.BB;
+      float a = 0.f;
+      const float t = (float)(-BB / (2 * AA));
+      if (!(t <= NEAR_PLANE)) {
+        const double min_value = fma(-BB / AA, BB / 4., (double)v2g[9]);
+        float power = (float)(-0.5 * min_value);
+        if (power > 0.0f) power = 0.0f;
+        const float alpha = fminf(0.99f, opacity * expf(power));
+        if (!(alpha < 1.0f / 255.0f)) a = alpha;
+      }
+      out[(size_t)py * W + px] = a;
+    }
+}

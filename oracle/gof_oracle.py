@@ -189,3 +189,10 @@ def mark_visible(means3D, viewmatrix):
     out = np.zeros(m.shape[0], np.uint8)
     _lib.oracle_mark_visible(int(m.shape[0]), _p(m), _p(_np(viewmatrix)), _p(out))
     return out.astype(bool)
+
+
+def alpha_map(W, H, tan_fovx, tan_fovy, v2g, opacity):
+    out = np.zeros((H, W), np.float32)
+    v = np.ascontiguousarray(v2g, np.float32)
+    _lib.oracle_alpha_map(int(W), int(H), ctypes.c_float(tan_fovx), ctypes.c_float(tan_fovy), _p(v), ctypes.c_float(float(opacity)), _p(out))
+    return out

@@ -52,4 +52,4 @@ def test_full_size_against_live_reference(ref, name, view):
     for n, a, b, c in zip(NAMES, go, g1, g2):
         noise = _util.rel_err(c, b)[0]
         err = _util.rel_err(a, b)[0]
-        assert err <= max(1e-4, 4.0 * noise), f"{n}: ours-vs-ref {err}, ref-vs-ref {noise}"
+        assert err <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {err}, ref-vs-ref {noise}"

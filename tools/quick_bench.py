@@ -48,6 +48,13 @@ def main():
             ba = _util.bwd_args(fa, radii, geom, R, binning, img, grad)
             t_b = time_it(lambda: mod.rasterize_gaussians_backward(*ba))
             res[label] = {"fwd_ms": t_f, "bwd_ms": t_b, "R": R, "visible": int((radii > 0).sum())}
+            if label == "ours":
+                ours.profile_reset(); ours.profile_enable(True)
+                for _ in range(3):
+                    o = mod.rasterize_gaussians(*fa)
+                    mod.rasterize_gaussians_backward(*_util.bwd_args(fa, o[2], o[3], o[0], o[4], o[5], grad))
+                torch.cuda.synchronize(); ours.profile_enable(False)
+                res[label]["kernels_ms"] = {k: round(v[1] / 3, 4) for k, v in sorted(ours.profile_report().items(), key=lambda kv: -kv[1][1])}
         out[name] = res
         print(name, json.dumps(res), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
