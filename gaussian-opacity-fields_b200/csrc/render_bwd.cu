@@ -7,6 +7,8 @@
 // the forward's operation sequence (gof_math.cuh) so that the recomputed alpha equals the forward's; the
 // traversal starts at the last Gaussian any pixel of the tile actually blended, warps skip Gaussians behind
 // their own deepest contributor and Gaussians whose alpha-support box (gof_cull_bbox) misses their pixels.
+#include <stdlib.h>
+
 #include "gof_common.cuh"
 #include "gof_math.cuh"
 
@@ -68,8 +70,8 @@ __device__ __forceinline__ float warp_reduce16(const float (&a)[16], int lane) {
   return e;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(GOF_BLOCK_SIZE, 3) k_render_backward(const BwdArgs a) {
+template <bool STATS, int MINB>
+__global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const BwdArgs a) {
   unsigned long long st_visit = 0, st_eval = 0, st_pass = 0, st_contrib = 0, st_anyhit = 0;
   __shared__ float4 s_rec[BATCH][4];
   __shared__ float4 s_recb[BATCH][2];
@@ -203,10 +205,11 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, 3) k_render_backward(const Bwd
         for (int q = 0; q < 16; ++q) g[q] = 0.f;
         if (contrib) {
           // backward.cu:806-817
-          const float mt = gof_mapped_t(t);
-          const float dm_dt = 20.0f / ((99.8f * t) * t);
-          const float len = gof_normal_length(p);
-          const float rlen = 1.0f / len;
+          const float mt = gof_mapped_t_fast(t);
+          const float dm_dt = F_DIV(20.0f / 99.8f, t * t);
+          // IEEE single-precision sqrt and reciprocal (not rsqrt): these feed dL_dview2gaussian, whose chain rule
+          // amplifies every ulp by ~1/scale^2
+          const float rlen = F_RCP(F_SQRT(F_FMA(p.n2, p.n2, F_FMA(p.n0, p.n0, F_MUL(p.n1, p.n1))) + 1e-7f));
           const float nn0 = -p.n0 * rlen, nn1 = -p.n1 * rlen, nn2 = -p.n2 * rlen;
           T = T / (1.f - alpha);
           const float w = alpha * T;
@@ -311,8 +314,12 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, const cha
   a.plane = (size_t)v.tiles * 256;
   a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g;
   a.stats = gof_stats_buffer();
-  if (a.stats) GOF_LAUNCH("render_bwd", st, k_render_backward<true><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
-  else GOF_LAUNCH("render_bwd", st, k_render_backward<false><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  static int occ = -1;   // GOF_BWD_OCC=2|3|4 (tuning knob)
+  if (occ < 0) { const char* e = getenv("GOF_BWD_OCC"); occ = e ? atoi(e) : 4; }
+  if (a.stats) GOF_LAUNCH("render_bwd", st, k_render_backward<true, 3><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  else if (occ >= 4) GOF_LAUNCH("render_bwd", st, k_render_backward<false, 4><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  else if (occ <= 2) GOF_LAUNCH("render_bwd", st, k_render_backward<false, 2><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  else GOF_LAUNCH("render_bwd", st, k_render_backward<false, 3><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }

@@ -9,7 +9,13 @@
 //    the Gaussians that can touch it;
 //  * a conservative single-precision pre-test discards pairs whose alpha is provably < 1/255 before the
 //    reference's double-precision evaluation; every pair that survives is evaluated with exactly the
-//    reference's operation sequence (gof_math.cuh), so accepted alphas are bit-identical.
+//    reference's operation sequence (gof_math.cuh), so t, power, alpha, T -- everything a threshold or a
+//    per-pixel counter depends on -- are bit-identical;
+//  * the quantities that only feed float outputs (mapped depth of the distortion term, the normalised normal)
+//    use cheaper evaluations accurate to ~1e-16 / 2e-7 instead of a double division, a double sqrt and three
+//    IEEE float divisions per blended pair.
+#include <stdlib.h>
+
 #include "gof_common.cuh"
 #include "gof_math.cuh"
 
@@ -36,7 +42,8 @@ __device__ __forceinline__ bool box_hits(uint32_t lo, uint32_t hi, int wx0, int 
   return x0 <= wx1 && x1 >= wx0 && y0 <= wy1 && y1 >= wy0;
 }
 
-__global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const FwdArgs a) {
   __shared__ float4 s_rec[BATCH][4];   // 16 KB: the 64-byte records of the current batch
   __shared__ float s_thr[BATCH];       // -ln(255*opacity): the largest power that can still be rejected
 
@@ -134,9 +141,9 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE) k_render_forward(const FwdArgs
           continue;
         }
         // forward.cu:543-578 (accumulation order = the reference's SASS: fma onto T)
-        const float mt = gof_mapped_t(t);
-        const float len = gof_normal_length(p);
-        const float nn0 = F_DIV(p.n0, len), nn1 = F_DIV(p.n1, len), nn2 = F_DIV(p.n2, len);
+        const float mt = gof_mapped_t_fast(t);
+        const float rlen = gof_normal_rlen_fast(p);
+        const float nn0 = p.n0 * rlen, nn1 = p.n1 * rlen, nn2 = p.n2 * rlen;
         const float A = F_SUB(1.0f, T);
         const float m2 = F_MUL(mt, mt);
         const float err = F_FMA(-dist1, F_ADD(mt, mt), F_FMA(A, m2, dist2));
@@ -201,7 +208,10 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
   a.ncontrib = reinterpret_cast<uint32_t*>(img + IL.ncontrib);
   a.out_color = out_color;
   a.plane = (size_t)v.tiles * 256;
-  GOF_LAUNCH("render_fwd", st, k_render_forward<<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  static int occ = -1;   // GOF_FWD_OCC=3|4: resident CTAs per SM the kernel is compiled for (tuning knob)
+  if (occ < 0) { const char* e = getenv("GOF_FWD_OCC"); occ = e ? atoi(e) : 4; }
+  if (occ >= 4) GOF_LAUNCH("render_fwd", st, k_render_forward<4><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  else GOF_LAUNCH("render_fwd", st, k_render_forward<3><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }

@@ -8,6 +8,7 @@ loaded the import fails, and CPU tensors are rejected.
 """
 import ctypes
 import os
+import sys
 
 import torch
 
@@ -87,13 +88,62 @@ def _c(t, dtype=torch.float32):
     return t.contiguous()
 
 
+class _Pool:
+    """Recycles the opaque scratch tensors between calls.
+
+    The reference allocates three fresh byte tensors per forward (rasterize_points.cu:75-79) and lets torch's
+    caching allocator recycle them.  At 1080p / 1M Gaussians those are 130 + 50 + 35 MB blocks whose
+    allocation showed up as 0.1-2 ms of host time per call in front of the first kernel launch, so the shim
+    keeps them: a buffer handed out earlier is reused once nothing else references it any more (neither a
+    Python variable nor an autograd saved-tensor slot), which is exactly when the caching allocator could have
+    recycled it.  Keyed by (device, stream, role) so that reuse is ordered on one stream."""
+
+    def __init__(self, keep=4):
+        self.items, self.keep = {}, keep
+
+    def take(self, key, nbytes, device, slack=1.0):
+        lst = self.items.setdefault(key, [])
+        for t in lst:
+            # references: the list, the loop variable and getrefcount's argument; _use_count()==1: no C++ holder
+            if t.numel() >= nbytes and t._use_count() == 1 and sys.getrefcount(t) <= 3:
+                return t
+        cap = ((int(nbytes * slack) + (1 << 20) - 1) >> 20) << 20
+        t = torch.empty(max(cap, 1 << 20), dtype=torch.uint8, device=device)
+        # drop surplus idle buffers (identity-based: list.remove would compare tensors element-wise)
+        surplus = len(lst) + 1 - self.keep
+        if surplus > 0:
+            kept = []
+            for x in lst:
+                if surplus > 0 and x._use_count() == 1 and sys.getrefcount(x) <= 3:
+                    surplus -= 1
+                else:
+                    kept.append(x)
+            lst[:] = kept
+        lst.append(t)
+        return t
+
+
+_POOL = _Pool()
+_USE_POOL = os.environ.get("GOF_POOL", "1") != "0"
+
+
 class _Scratch:
-    """One opaque uint8 CUDA tensor grown by the library through the allocator callback
+    """One opaque uint8 CUDA tensor sized by the library through the allocator callback
     (resizeFunctional, rasterize_points.cu:28-34)."""
 
-    def __init__(self, device):
+    def __init__(self, device, role="", slack=1.0):
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = _ALLOC_FN(self._alloc)
+        self.cb = _ALLOC_FN(self._alloc_pooled if (_USE_POOL and role) else self._alloc)
+        self.role, self.slack = role, slack
+
+    def _alloc_pooled(self, _user, nbytes):
+        if not nbytes:
+            return 0
+        dev = self.tensor.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        key = (idx, torch.cuda.current_stream().cuda_stream, self.role)
+        self.tensor = _POOL.take(key, int(nbytes), dev, self.slack)
+        return self.tensor.data_ptr()
 
     def _alloc(self, _user, nbytes):
         # torch's caching allocator returns >= 512-byte aligned blocks
@@ -154,7 +204,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         out_color = torch.zeros((9, int(image_height), int(image_width)), dtype=torch.float32, device=dev)
         radii = torch.zeros((s.P,), dtype=torch.int32, device=dev)
         sdev = dev if means3D.is_cuda else torch.device("cuda")
-        geom, binning, img = _Scratch(sdev), _Scratch(sdev), _Scratch(sdev)
+        geom, binning, img = _Scratch(sdev, "geom"), _Scratch(sdev, "binning", 1.25), _Scratch(sdev, "image")
         rendered = ctypes.c_int(0)
         if s.P != 0:
             _check(_lib.gof_rasterize_forward(ctypes.byref(s), geom.cb, None, binning.cb, None, img.cb, None,
@@ -180,6 +230,20 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     M = s.M
     o = dict(dtype=means3D.dtype, device=means3D.device)
 
+    # One zero-filled block for all gradient tensors (one fill instead of the reference's ten torch::zeros,
+    # rasterize_points.cu:161-170); every tensor is a contiguous, 256-byte aligned view of it.
+    shapes = dict(dmeans3D=(P, 3), dmeans2D=(P, 3), dcolors=(P, 3), dopacity=(P, 1), dcov3D=(P, 6), dsh=(P, M, 3),
+                  dscales=(P, 3), drot=(P, 4), dv2g=(P, 10))
+    need = {k: v for k, v in shapes.items() if not (_out is not None and k in _out)}
+    offs, total = {}, 0
+    for k, shp in need.items():
+        offs[k] = total
+        n = 1
+        for d in shp:
+            n *= d
+        total += (n + 63) // 64 * 64
+    block = torch.zeros(max(total, 1), **o)
+
     def _z(name, shape):
         # `_out` (extension, used by gof_dp.GradBucket): pre-zeroed, contiguous destination tensors, e.g. views
         # of one flat all-reduce buffer, so the backward writes straight into the communication buffer
@@ -187,7 +251,10 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             t = _out[name]
             assert t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.dtype == means3D.dtype
             return t
-        return torch.zeros(shape, **o)
+        n = 1
+        for d in shape:
+            n *= d
+        return block[offs[name]:offs[name] + n].view(shape)
 
     dL_dmeans3D = _z("dmeans3D", (P, 3))
     dL_dmeans2D = _z("dmeans2D", (P, 3))
