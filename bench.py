@@ -405,9 +405,15 @@ def main():
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 rasterizer has no CPU path")
+    # keep stdout clean for the ONE JSON line (NCCL prints its version banner to stdout): everything else -> stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local if world > 1 else 0)
     line = run_ours(args, rank, world, dev) if args.impl == "ours" else run_reference(args, rank, world, dev)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
