@@ -315,12 +315,57 @@ extern "C" int gof_export_state(int P, int width, int height, int num_rendered, 
   return GOF_OK;
 }
 
-// ---- not yet built in this revision -------------------------------------------------------------------
-extern "C" int gof_integrate(const gof_scene_t*, int, const float*, gof_alloc_fn, void*, gof_alloc_fn, void*,
-                             gof_alloc_fn, void*, gof_alloc_fn, void*, gof_alloc_fn, void*, float*, int*, float*,
-                             float*, int*, void*) {
-  gof_set_error("gof_integrate: not implemented in this build");
-  return GOF_E_INVALID;
+// Rasterizer::integrate (rasterizer_impl.cu:530-792): Gaussian side exactly as the forward (preprocess, depth sort,
+// binning), then the point side and the query kernel.
+extern "C" int gof_integrate(const gof_scene_t* s, int PN, const float* points3D, gof_alloc_fn geom_alloc, void* geom_user,
+                             gof_alloc_fn binning_alloc, void* binning_user, gof_alloc_fn image_alloc, void* image_user,
+                             gof_alloc_fn point_alloc, void* point_user, gof_alloc_fn point_binning_alloc,
+                             void* point_binning_user, float* out_color, int* radii, float* out_alpha_integrated,
+                             float* out_color_integrated, int* num_rendered, void* stream) {
+  int rc = validate_scene(s);
+  if (rc != GOF_OK) return rc;
+  if (!geom_alloc || !binning_alloc || !image_alloc || !point_alloc || !point_binning_alloc || !num_rendered) {
+    gof_set_error("integrate: allocators / num_rendered must be non-NULL");
+    return GOF_E_INVALID;
+  }
+  *num_rendered = 0;
+  if (s->P == 0 || PN <= 0) return GOF_OK;   // rasterize_points.cu:305
+  if (!points3D || !out_color || !radii || !out_alpha_integrated || !out_color_integrated) {
+    gof_set_error("integrate: NULL argument");
+    return GOF_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const GofView v = gof_make_view(s);
+  const GofGeomLayout GL = gof_geom_layout((size_t)s->P);
+  char* geom = (char*)geom_alloc(geom_user, GL.bytes);
+  const GofImageLayout IL = gof_image_layout(s->width, s->height);
+  char* img = (char*)image_alloc(image_user, IL.bytes);
+  if (!geom || !img) { gof_set_error("scratch allocator returned NULL"); return GOF_E_ALLOC; }
+  if ((rc = gof_launch_preprocess(s, v, geom, GL, radii, st)) != GOF_OK) return rc;
+  if ((rc = gof_depth_sort_and_offsets(s->P, geom, GL, s->debug != 0, st)) != GOF_OK) return rc;
+  uint32_t R = 0;
+  GOF_CUDA_OK(cudaMemcpyAsync(&R, geom + GL.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  *num_rendered = (int)R;
+  const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height);
+  char* bin = (char*)binning_alloc(binning_user, BL.bytes);
+  if (!bin && BL.bytes) { gof_set_error("binning allocator returned NULL"); return GOF_E_ALLOC; }
+  if ((rc = gof_bin_tiles(s->P, (size_t)R, v, geom, GL, bin, BL, img, IL, s->debug != 0, st)) != GOF_OK) return rc;
+
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  const GofPointLayout PL = gof_point_layout((size_t)PN);
+  const GofPointBinLayout PBL = gof_point_bin_layout((size_t)PN, v.tiles, sm_count);
+  char* pts = (char*)point_alloc(point_user, PL.bytes);
+  char* pbin = (char*)point_binning_alloc(point_binning_user, PBL.bytes);
+  if (!pts || !pbin) { gof_set_error("point allocator returned NULL"); return GOF_E_ALLOC; }
+  return gof_launch_integrate(s, v, PN, points3D, geom, GL, bin, BL, img, IL, pts, PL, pbin, PBL, out_color,
+                              out_alpha_integrated, out_color_integrated, st);
 }
 extern "C" int gof_marching_tets_count(int, const float*, int64_t, const int64_t*, gof_alloc_fn, void*, int64_t*,
                                        int64_t*, void*) {

@@ -365,6 +365,30 @@ int gof_depth_sort_and_offsets(int P, char* geom, const GofGeomLayout& L, bool d
                                     reinterpret_cast<uint32_t*>(geom + L.total), debug, st);
 }
 
+// Stable sort of `n` (tile id, index) pairs by tile id (ids < 2^nbits) for the integrate path's query points, then
+// the per-tile ranges of the first ids < num_tiles (ranges must hold num_tiles + 1 uint2; the last slot absorbs the
+// sentinel id given to points outside the image).  Buffers: keys/vals ping-pong (u32), hist as in gof_bin_layout.
+int gof_sort_points_by_tile(size_t n, int nbits, uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist,
+                            uint2* ranges, int num_tiles, bool debug, cudaStream_t st, int* result_in_b) {
+  GOF_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)(num_tiles + 1) * sizeof(uint2), st));
+  *result_in_b = 0;
+  if (n == 0) return GOF_OK;
+  const int passes = (nbits + 7) / 8;
+  int shift = 0, rem = nbits;
+  for (int p = 0; p < passes; ++p) {
+    const int b = (rem + (passes - p) - 1) / (passes - p);
+    const bool a2b = (p % 2 == 0);
+    int rc = radix_pass<uint32_t>(a2b ? ka : kb, a2b ? va : vb, a2b ? kb : ka, a2b ? vb : va, n, shift, b, hist, debug, st);
+    if (rc != GOF_OK) return rc;
+    shift += b; rem -= b;
+  }
+  *result_in_b = passes % 2;
+  const uint32_t* sorted = (passes % 2) ? kb : ka;
+  GOF_LAUNCH("tile_ranges", st, k_tile_ranges<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, sorted, ranges));
+  GOF_LAUNCH_CHECK(debug, st);
+  return GOF_OK;
+}
+
 int gof_bin_tiles(int P, size_t R, const GofView& v, char* geom, const GofGeomLayout& GL, char* bin,
                   const GofBinLayout& BL, char* img, const GofImageLayout& IL, bool debug, cudaStream_t st) {
   if (BL.key_bytes == 2) return bin_tiles_t<uint16_t>(P, R, v, geom, GL, bin, BL, img, IL, debug, st);

@@ -210,6 +210,34 @@ int gof_depth_sort_and_offsets(int P, char* geom, const GofGeomLayout& L, bool d
 int gof_bin_tiles(int P, size_t R, const GofView& v, char* geom, const GofGeomLayout& GL, char* bin,
                   const GofBinLayout& BL, char* img, const GofImageLayout& IL, bool debug, cudaStream_t st);
 
+int gof_sort_points_by_tile(size_t n, int nbits, uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist,
+                            uint2* ranges, int num_tiles, bool debug, cudaStream_t st, int* result_in_b);
+
+// integrate.cu
+struct GofPointLayout { size_t xy, depth, bytes; };
+struct GofPointBinLayout { size_t key_a, key_b, val_a, val_b, hist, pranges, ids, bytes; int nblk; };
+static inline GofPointLayout gof_point_layout(size_t PN) {
+  GofPointLayout L; size_t o = 0;
+  auto take = [&](size_t b) { size_t r = o; o = gof_align_up(o + b, 256); return r; };
+  L.xy = take(PN * 8); L.depth = take(PN * 4); L.bytes = o; return L;
+}
+#define GOF_INT_MAX_CONTRIB 1024   // MAX_NUM_CONTRIBUTORS * 4 (auxiliary.h:26, forward.cu:879)
+static inline GofPointBinLayout gof_point_bin_layout(size_t PN, int tiles, int sm_count) {
+  GofPointBinLayout L; size_t o = 0;
+  auto take = [&](size_t b) { size_t r = o; o = gof_align_up(o + b, 256); return r; };
+  L.key_a = take(PN * 4); L.key_b = take(PN * 4); L.val_a = take(PN * 4); L.val_b = take(PN * 4);
+  L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(PN) + 1) * 4);
+  L.pranges = take((size_t)(tiles + 1) * 8);
+  L.nblk = tiles < sm_count * 3 ? tiles : sm_count * 3;
+  if (L.nblk < 1) L.nblk = 1;
+  L.ids = take((size_t)L.nblk * 256 * GOF_INT_MAX_CONTRIB * 2);
+  L.bytes = o; return L;
+}
+int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const float* points3D, const char* geom,
+                         const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL, char* img, const GofImageLayout& IL,
+                         char* pts, const GofPointLayout& PL, char* pbin, const GofPointBinLayout& PBL, float* out_color,
+                         float* out_alpha, float* out_color_int, cudaStream_t st);
+
 // render_fwd.cu / render_bwd.cu
 int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char* geom,
                               const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL, char* img,

@@ -765,3 +765,167 @@ void oracle_alpha_map(int W, int H, float tan_fovx, float tan_fovy, const float*
       out[(size_t)py * W + px] = a;
     }
 }
+
+/* =====================================================================================================
+ * Opacity-field query ("integrate"): forward.cu:722-766 preprocessPointsCUDA, rasterizer_impl.cu:113-144
+ * createWithKeys, forward.cu:803-1218 integrateCUDA.
+ *
+ * The five sub-pixel rays of pass 1 are unrolled by nvcc and share products between rays, so each ray ends up
+ * with its own fusion pattern in the reference's SASS; pass 2 evaluates  -1/2 (A t^2 + B t + C)  entirely in
+ * float (C ~ 1e5..1e6), so its value is defined by that exact sequence.  Both are restated below.
+ * ===================================================================================================== */
+
+/* forward.cu:722-766: returns 1 and fills xy/depth when the point projects inside the image */
+static int point_project(const float* p, const float* vm, int W, int H, float focal_x, float focal_y, float* xy, float* depth) {
+  const float tz = affine(p[0], p[1], p[2], vm[2], vm[6], vm[10], vm[14]);
+  if (tz <= 0.2f) return 0;
+  const float tx = affine(p[0], p[1], p[2], vm[0], vm[4], vm[8], vm[12]);
+  const float ty = affine(p[0], p[1], p[2], vm[1], vm[5], vm[9], vm[13]);
+  const float x = (float)((double)((focal_x * tx) / (tz + 0.0000001f)) + W / 2.);
+  const float y = (float)((double)((focal_y * ty) / (tz + 0.0000001f)) + H / 2.);
+  if (x < 0 || x >= W || y < 0 || y >= H) return 0;
+  xy[0] = x; xy[1] = y; *depth = tz;
+  return 1;
+}
+
+/* the five rays of forward.cu:919-930 with the reference's per-ray fusion (k = 0: centre, 1..4: corners) */
+static void pair_geom_k(int k, const float* v, float rx, float ry, float* n, float* AA, float* BB) {
+  float n0, n1, n2, bh;
+  if (k == 0) {
+    n0 = fmaf(rx, v[0], ry * v[1]) + v[2];
+    n1 = fmaf(rx, v[1], ry * v[3]) + v[4];
+    n2 = fmaf(ry, v[4], rx * v[2]) + v[5];
+    bh = fmaf(rx, v[6], ry * v[7]) + v[8];
+  } else {
+    n0 = (rx * v[0] + ry * v[1]) + v[2];
+    n1 = (k == 1 || k == 3) ? fmaf(rx, v[1], ry * v[3]) + v[4] : (ry * v[3] + rx * v[1]) + v[4];
+    n2 = fmaf(rx, v[2], ry * v[4]) + v[5];
+    bh = (rx * v[6] + ry * v[7]) + v[8];
+  }
+  n[0] = n0; n[1] = n1; n[2] = n2;
+  *AA = fmaf(rx, n0, ry * n1) + n2;
+  *BB = bh + bh;
+}
+
+#define MAX_CONTRIB 1024 /* MAX_NUM_CONTRIBUTORS * 4, forward.cu:879,986 */
+
+/* Whole integrate for one view.  Inputs: Gaussian state + tile lists from oracle_preprocess / oracle_bin.
+ * out_color [9,H,W] (channels 0-2, 6, 7, 8 written), final_T [H,W], n_contrib [H,W],
+ * out_alpha_integrated [PN] (caller-initialised to 1), out_color_integrated [PN,3] (caller-initialised to 0). */
+void oracle_integrate(int W, int H, float tan_fovx, float tan_fovy, const float* viewmatrix, int PN, const float* points3D,
+                      const uint32_t* ranges, const uint32_t* point_list, const float* features, const float* view2gaussian,
+                      const float* conic_opacity, const float* bg, float* out_color, float* final_T, uint32_t* n_contrib,
+                      float* out_alpha_integrated, float* out_color_integrated) {
+  const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
+  const int gx = (W + BLOCK_X - 1) / BLOCK_X;
+  const size_t HW = (size_t)H * W;
+  /* bucket the projected points per pixel (which pixel handles a point: forward.cu:1071-1072) */
+  float* pxy = (float*)malloc((size_t)PN * 2 * sizeof(float));
+  float* pdepth = (float*)malloc((size_t)PN * sizeof(float));
+  int* ppix = (int*)malloc((size_t)PN * sizeof(int));
+  uint32_t* cnt = (uint32_t*)calloc(HW + 1, sizeof(uint32_t));
+  for (int i = 0; i < PN; ++i) {
+    ppix[i] = -1;
+    if (point_project(points3D + 3 * (size_t)i, viewmatrix, W, H, focal_x, focal_y, pxy + 2 * (size_t)i, pdepth + i)) {
+      const int px = (int)pxy[2 * (size_t)i], py = (int)pxy[2 * (size_t)i + 1];
+      ppix[i] = py * W + px;
+      cnt[ppix[i] + 1]++;
+    }
+  }
+  for (size_t i = 0; i < HW; ++i) cnt[i + 1] += cnt[i];
+  uint32_t* order = (uint32_t*)malloc(((size_t)cnt[HW] + 1) * sizeof(uint32_t));
+  uint32_t* cur = (uint32_t*)malloc(HW * sizeof(uint32_t));
+  memcpy(cur, cnt, HW * sizeof(uint32_t));
+  for (int i = 0; i < PN; ++i)
+    if (ppix[i] >= 0) order[cur[ppix[i]]++] = (uint32_t)i;
+
+  static const float offx[5] = {0.0f, -0.5f, 0.5f, -0.5f, 0.5f};
+  static const float offy[5] = {0.0f, -0.5f, -0.5f, 0.5f, 0.5f};
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int py = 0; py < H; ++py) {
+    uint16_t* ids = (uint16_t*)malloc(MAX_CONTRIB * sizeof(uint16_t));
+    for (int px = 0; px < W; ++px) {
+      const size_t pix_id = (size_t)W * py + px;
+      const float pixfx = (float)px + 0.5f, pixfy = (float)py + 0.5f;
+      const uint32_t* range = ranges + 2 * ((py / BLOCK_Y) * gx + (px / BLOCK_X));
+      float rxk[5], ryk[5];
+      for (int k = 0; k < 5; ++k) {
+        rxk[k] = (float)((pixfx + offx[k] - W / 2.) / focal_x);
+        ryk[k] = (float)((pixfy + offy[k] - H / 2.) / focal_y);
+      }
+      float Ts[5] = {1, 1, 1, 1, 1};
+      float C[8] = {0};
+      uint32_t contributor = 0, last_contributor = 0, n_local = 0;
+      /* pass 1, forward.cu:886-993 */
+      for (uint32_t kk = range[0]; kk < range[1]; ++kk) {
+        contributor++;
+        const uint32_t gid = point_list[kk];
+        const float* v = view2gaussian + 10 * (size_t)gid;
+        const float opac = conic_opacity[4 * (size_t)gid + 3];
+        int used = 0;
+        for (int k = 0; k < 5; ++k) {
+          float nrm[3], AA, BB;
+          pair_geom_k(k, v, rxk[k], ryk[k], nrm, &AA, &BB);
+          const float CC = v[9];
+          const float t = -BB / (2 * AA);
+          if (t <= NEAR_PLANE) continue;
+          const double min_value = fma((double)(-BB / AA), (double)BB / 4., (double)CC);
+          float power = (float)(-0.5 * min_value);
+          if (power > 0.0f) power = 0.0f;
+          const float alpha = fminf(0.99f, opac * expf(power));
+          if (alpha < 1.0f / 255.0f) continue;
+          const float test_T = Ts[k] * (1 - alpha);
+          if (test_T < 0.0001f) continue;
+          if (k == 0)
+            for (int ch = 0; ch < 3; ++ch) C[ch] = fmaf(Ts[0], alpha * features[3 * (size_t)gid + ch], C[ch]);
+          if (t > C[6]) C[6] = t;
+          if (k == 0) C[7] = fmaf(Ts[0], alpha, C[7]);
+          Ts[k] = test_T;
+          used = 1;
+        }
+        if (used) {
+          last_contributor = contributor;
+          ids[n_local++] = (uint16_t)contributor;
+          if (n_local >= MAX_CONTRIB) break;
+        }
+      }
+      final_T[pix_id] = Ts[0];
+      n_contrib[pix_id] = last_contributor;
+      float col[3];
+      for (int ch = 0; ch < 3; ++ch) { col[ch] = fmaf(Ts[0], bg[ch], C[ch]); out_color[ch * HW + pix_id] = col[ch]; }
+      out_color[6 * HW + pix_id] = C[6];
+      out_color[7 * HW + pix_id] = C[7];
+      /* pass 2, forward.cu:1116-1210: every point of this pixel against the recorded contributors */
+      const uint32_t p0 = cnt[pix_id], p1 = cnt[pix_id + 1];
+      for (uint32_t q = p0; q < p1; ++q) {
+        const uint32_t id = order[q];
+        const float rx = (float)(((double)pxy[2 * (size_t)id] - W / 2.) / focal_x);
+        const float ry = (float)(((double)pxy[2 * (size_t)id + 1] - H / 2.) / focal_y);
+        const float ray_depth = pdepth[id];
+        float point_alpha = 0.f, point_T = 1.f;
+        uint32_t num_iterated = 0, second = 0;
+        for (uint32_t kk = range[0]; kk < range[1]; ++kk) {
+          num_iterated++;
+          if (num_iterated > last_contributor) break;
+          if (second >= n_local || num_iterated != (uint32_t)ids[second]) continue;
+          second++;
+          const uint32_t gid = point_list[kk];
+          const float* v = view2gaussian + 10 * (size_t)gid;
+          const pair_t p = pair_geom(v, rx, ry);
+          float t = -p.BB / (2 * p.AA);
+          if (t > ray_depth) t = ray_depth;
+          const float power = -0.5f * (v[9] + fmaf(p.BB, t, (p.AA * t) * t));
+          const float alpha = fminf(0.99f, conic_opacity[4 * (size_t)gid + 3] * expf(power));
+          if (alpha < 1.0f / 255.0f) continue;
+          point_alpha = fmaf(alpha, point_T, point_alpha);
+          point_T = point_T * (1 - alpha);
+        }
+        out_alpha_integrated[id] = point_alpha;
+        for (int ch = 0; ch < 3; ++ch) out_color_integrated[3 * (size_t)id + ch] = col[ch];
+      }
+      out_color[8 * HW + pix_id] = (float)(p1 - p0);
+    }
+    free(ids);
+  }
+  free(pxy); free(pdepth); free(ppix); free(cnt); free(order); free(cur);
+}

@@ -196,3 +196,27 @@ def alpha_map(W, H, tan_fovx, tan_fovy, v2g, opacity):
     v = np.ascontiguousarray(v2g, np.float32)
     _lib.oracle_alpha_map(int(W), int(H), ctypes.c_float(tan_fovx), ctypes.c_float(tan_fovy), _p(v), ctypes.c_float(float(opacity)), _p(out))
     return out
+
+
+def integrate(scene, points3D):
+    """Opacity-field query of `points3D` [PN,3] for one view: (out_color[9,H,W], alpha_integrated[PN],
+    color_integrated[PN,3], radii[P], state) -- the 4 tensors GaussianRasterizer.integrate returns, plus state."""
+    g = preprocess(scene)
+    R, point_list, ranges = bin_tiles(scene.W, scene.H, g["radii"], g["means2D"], g["depths"], g["tiles_touched"])
+    pts = _np(points3D)
+    PN = int(pts.shape[0])
+    W, H = scene.W, scene.H
+    out = np.zeros((9, H, W), np.float32)
+    final_T = np.zeros((H, W), np.float32)
+    n_contrib = np.zeros((H, W), np.uint32)
+    alpha_int = np.ones(PN, np.float32)
+    color_int = np.zeros((PN, 3), np.float32)
+    if scene.P and PN:
+        _lib.oracle_integrate(W, H, ctypes.c_float(scene.tan_fovx), ctypes.c_float(scene.tan_fovy), _p(scene.arr["viewmatrix"]),
+                              PN, _p(pts), _p(np.ascontiguousarray(ranges, np.uint32)), _p(np.ascontiguousarray(point_list, np.uint32)),
+                              _p(np.ascontiguousarray(g["rgb"], np.float32)), _p(np.ascontiguousarray(g["view2gaussian"], np.float32)),
+                              _p(np.ascontiguousarray(g["conic_opacity"], np.float32)), _p(scene.arr["background"]), _p(out),
+                              _p(final_T), _p(n_contrib), _p(alpha_int), _p(color_int))
+    st = dict(g)
+    st.update(num_rendered=R, point_list=point_list, ranges=ranges, final_T=final_T, n_contrib=n_contrib)
+    return out, alpha_int, color_int, g["radii"], st

@@ -88,6 +88,17 @@ def main():
             out["grad_" + n] = runs[0][i]
             a = np.stack([r[i] for r in runs]).astype(np.float64)
             out["gradnoise_" + n] = np.float64(np.abs(a - a[0]).max() / max(np.abs(a[0]).max(), 1e-30)) if a.size else np.float64(0)
+        # ---- opacity-field query (GaussianRasterizer.integrate -> _C.integrate_gaussians_to_points) ----
+        gp = torch.Generator().manual_seed(cfg["seed"] + 21)
+        npts = 3000
+        near = gs["means3D"][torch.randint(0, P, (npts // 2,), generator=gp)] + 0.02 * torch.randn(npts // 2, 3, generator=gp)
+        pts = torch.cat([near, (torch.rand(npts - npts // 2, 3, generator=gp) * 2 - 1) * 1.5]).contiguous()
+        ia = (fa[0], pts.to(dev)) + tuple(fa[1:])
+        iR, icolor, ialpha, icol, iradii, igeom, ibin, iimg = ref.integrate_gaussians_to_points(*ia)
+        ii = _util.carve_ref_image(iimg, W, H)
+        out.update(int_points=pts.numpy(), int_color=icolor.cpu().numpy(), int_alpha=ialpha.cpu().numpy(),
+                   int_color_integrated=icol.cpu().numpy(), int_n_contrib=ii["n_contrib"][0].cpu().numpy(),
+                   int_final_T=ii["accum_alpha"][0].cpu().numpy())
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
         print(name, "R", R, "visible", int(vis.sum()), "max tile list", int((si["ranges"][:, 1] - si["ranges"][:, 0]).max()),
               {n: float(out["gradnoise_" + n]) for n in names})
