@@ -367,13 +367,3 @@ extern "C" int gof_integrate(const gof_scene_t* s, int PN, const float* points3D
   return gof_launch_integrate(s, v, PN, points3D, geom, GL, bin, BL, img, IL, pts, PL, pbin, PBL, out_color,
                               out_alpha_integrated, out_color_integrated, st);
 }
-extern "C" int gof_marching_tets_count(int, const float*, int64_t, const int64_t*, gof_alloc_fn, void*, int64_t*,
-                                       int64_t*, void*) {
-  gof_set_error("gof_marching_tets_count: not implemented in this build");
-  return GOF_E_INVALID;
-}
-extern "C" int gof_marching_tets_emit(int, const float*, int64_t, const int64_t*, const void*, int64_t, int64_t,
-                                      int64_t*, int64_t*, void*) {
-  gof_set_error("gof_marching_tets_emit: not implemented in this build");
-  return GOF_E_INVALID;
-}

@@ -389,6 +389,31 @@ int gof_sort_points_by_tile(size_t n, int nbits, uint32_t* ka, uint32_t* kb, uin
   return GOF_OK;
 }
 
+// Stable LSD radix sort of n (u32 key, u32 value) pairs on the low `nbits` key bits.  Ping-pong buffers a/b (input in a);
+// *result_in_b tells where the result is.  hist: GOF_RADIX * (gof_sort_blocks(n) + 1) u32.
+int gof_sort_pairs_u32(uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist, size_t n, int nbits, bool debug,
+                       cudaStream_t st, int* result_in_b) {
+  *result_in_b = 0;
+  if (n == 0 || nbits <= 0) return GOF_OK;
+  const int passes = (nbits + 7) / 8;
+  int shift = 0, rem = nbits;
+  for (int p = 0; p < passes; ++p) {
+    const int b = (rem + (passes - p) - 1) / (passes - p);
+    const bool a2b = (p % 2 == 0);
+    int rc = radix_pass<uint32_t>(a2b ? ka : kb, a2b ? va : vb, a2b ? kb : ka, a2b ? vb : va, n, shift, b, hist, debug, st);
+    if (rc != GOF_OK) return rc;
+    shift += b; rem -= b;
+  }
+  *result_in_b = passes % 2;
+  return GOF_OK;
+}
+
+// exclusive scan of n u32 (in != out allowed); total (if non-NULL) receives the sum; tmp: n/2048 + 2 u32
+int gof_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t* tmp, uint32_t* total, size_t n, bool debug, cudaStream_t st) {
+  LoadDirect ld{in};
+  return scan_u32<LoadDirect, false>(ld, n, out, tmp, total, debug, st);
+}
+
 int gof_bin_tiles(int P, size_t R, const GofView& v, char* geom, const GofGeomLayout& GL, char* bin,
                   const GofBinLayout& BL, char* img, const GofImageLayout& IL, bool debug, cudaStream_t st) {
   if (BL.key_bytes == 2) return bin_tiles_t<uint16_t>(P, R, v, geom, GL, bin, BL, img, IL, debug, st);

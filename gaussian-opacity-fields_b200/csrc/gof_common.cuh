@@ -203,9 +203,9 @@ int gof_launch_mark_visible(int P, const float* means3D, const float* vm, unsign
                             cudaStream_t st);
 
 // binning.cu
-int gof_sort_pairs_u32(const uint32_t* keys_in, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a,
-                       uint32_t* vals_b, uint32_t* hist, size_t n, int begin_bit, int end_bit, bool debug,
+int gof_sort_pairs_u32(uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist, size_t n, int nbits, bool debug,
                        cudaStream_t st, int* result_in_b);
+int gof_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t* tmp, uint32_t* total, size_t n, bool debug, cudaStream_t st);
 int gof_depth_sort_and_offsets(int P, char* geom, const GofGeomLayout& L, bool debug, cudaStream_t st);
 int gof_bin_tiles(int P, size_t R, const GofView& v, char* geom, const GofGeomLayout& GL, char* bin,
                   const GofBinLayout& BL, char* img, const GofImageLayout& IL, bool debug, cudaStream_t st);

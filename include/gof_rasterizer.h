@@ -139,13 +139,20 @@ GOF_API int gof_export_state(int P, int width, int height, int num_rendered,
                      const int* radii, const gof_state_view_t* out, void* stream);
 
 /* Marching tetrahedra, utils/tetmesh.py:47-138 (_unbatched_marching_tetrahedra), as CUDA.
- * Two-phase: count (returns sizes on the host), then emit into caller-allocated outputs. */
-GOF_API int gof_marching_tets_count(int num_verts, const float* sdf, int64_t num_tets, const int64_t* tets,
-                            gof_alloc_fn scratch_alloc, void* scratch_user,
-                            int64_t* num_edges_out, int64_t* num_faces_out, void* stream);
-GOF_API int gof_marching_tets_emit(int num_verts, const float* sdf, int64_t num_tets, const int64_t* tets,
-                           const void* scratch, int64_t num_edges, int64_t num_faces,
-                           int64_t* interp_v /* [E,2] */, int64_t* faces /* [F,3] */, void* stream);
+ * Two phases because the output sizes are data dependent: `count` classifies the tets, emits and sorts the crossing
+ * edges and returns the number of unique crossing edges E and of faces F on the host; `emit` then fills
+ * caller-allocated outputs.  `chunk_tets` reproduces the reference's chunked face order (its chunk_size of
+ * 32*1024*1024, tetmesh.py:55); pass 0 for "one chunk".  tets: [T,4] int64 vertex ids < 2^32.  Outputs:
+ * interp_v [E,2] int64 (sorted unique crossing edges), faces [F,3] int64; optional gathers of the edge endpoints:
+ * edge_pos [E,2,3] from vertices [V,3], edge_sdf [E,2], edge_scales [E,2] from scales [V] (any may be NULL). */
+GOF_API int gof_marching_tets_count(int num_verts, const float* sdf, int64_t num_tets, const int64_t* tets, int64_t chunk_tets,
+                                    gof_alloc_fn scratch_alloc, void* scratch_user,
+                                    int64_t* num_edges_out, int64_t* num_faces_out, void* stream);
+GOF_API int gof_marching_tets_emit(int num_verts, const float* sdf, int64_t num_tets, const int64_t* tets, int64_t chunk_tets,
+                                   void* scratch, int64_t num_edges, int64_t num_faces,
+                                   int64_t* interp_v /* [E,2] */, int64_t* faces /* [F,3] */,
+                                   const float* vertices, const float* scales,
+                                   float* edge_pos, float* edge_sdf, float* edge_scales, void* stream);
 
 /* Launch accounting and live per-kernel timing (CUDA events on the launching stream; not a profiler).
  * gof_launch_count(): kernels launched by this library so far.  gof_profile_report(): lines of

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def fixture_paths():
-    return sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+    return sorted(glob.glob(os.path.join(HERE, "golden", "f[0-9]_*.npz")))
 
 
 def load(path):
