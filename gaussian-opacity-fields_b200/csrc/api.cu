@@ -37,6 +37,8 @@ unsigned long long g_launches = 0;
 std::vector<ProfEntry> g_prof_pending;
 std::vector<cudaEvent_t> g_prof_pool;
 std::map<std::string, std::pair<unsigned long long, double>> g_prof_acc;   // name -> (count, ms)
+cudaEvent_t g_prof_base = nullptr;      // first bracket's start: origin of the timeline
+std::string g_prof_timeline;            // "name start_ms end_ms\n" per launch since the last reset
 thread_local ProfEntry g_prof_cur = {nullptr, nullptr, nullptr};
 cudaEvent_t prof_get_event() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
@@ -49,6 +51,13 @@ void prof_drain_locked() {
     cudaEventElapsedTime(&ms, e.a, e.b);
     auto& acc = g_prof_acc[e.name];
     acc.first += 1; acc.second += ms;
+    if (g_prof_base && g_prof_timeline.size() < (1u << 22)) {
+      float t0 = 0.f;
+      cudaEventElapsedTime(&t0, g_prof_base, e.a);
+      char line[160];
+      snprintf(line, sizeof(line), "%s %.4f %.4f\n", e.name, t0, t0 + ms);
+      g_prof_timeline += line;
+    }
     g_prof_pool.push_back(e.a); g_prof_pool.push_back(e.b);
   }
   g_prof_pending.clear();
@@ -60,6 +69,7 @@ void gof_prof_begin(const char* name, cudaStream_t st) {
   g_launches++;
   if (!g_prof_on) return;
   g_prof_cur.name = name; g_prof_cur.a = prof_get_event(); g_prof_cur.b = prof_get_event();
+  if (!g_prof_base) { cudaEventCreate(&g_prof_base); cudaEventRecord(g_prof_base, st); }
   cudaEventRecord(g_prof_cur.a, st);
 }
 void gof_prof_end(cudaStream_t st) {
@@ -80,6 +90,8 @@ extern "C" void gof_profile_reset(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   prof_drain_locked();
   g_prof_acc.clear();
+  g_prof_timeline.clear();
+  if (g_prof_base) { cudaEventDestroy(g_prof_base); g_prof_base = nullptr; }
 }
 // writes "name count total_ms\n" lines; returns the number of bytes needed (excluding the terminator)
 extern "C" int gof_profile_report(char* buf, int cap) {
@@ -95,6 +107,31 @@ extern "C" int gof_profile_report(char* buf, int cap) {
   return (int)out.size();
 }
 
+// writes "name start_ms end_ms\n" per bracketed launch (origin: the first launch after the last reset)
+extern "C" int gof_profile_timeline(char* buf, int cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  prof_drain_locked();
+  if (buf && cap > 0) { strncpy(buf, g_prof_timeline.c_str(), (size_t)cap - 1); buf[cap - 1] = 0; }
+  return (int)g_prof_timeline.size();
+}
+
+void* gof_pinned_slot() {
+  static thread_local void* slot = nullptr;
+  static thread_local bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (cudaHostAlloc(&slot, 64, cudaHostAllocDefault) != cudaSuccess) { slot = nullptr; (void)cudaGetLastError(); }
+  }
+  return slot;
+}
+int gof_read_back(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
+  void* pin = bytes <= 64 ? gof_pinned_slot() : nullptr;
+  GOF_CUDA_OK(cudaMemcpyAsync(pin ? pin : dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  if (pin) memcpy(dst, pin, bytes);
+  return GOF_OK;
+}
+
 static unsigned long long* g_stats_dev = nullptr;
 unsigned long long* gof_stats_buffer() {
   static int on = -1;
@@ -104,7 +141,7 @@ unsigned long long* gof_stats_buffer() {
   return g_stats_dev;
 }
 // copies the 8 counters to `out` (host) and clears them; returns 0 if statistics are disabled
-extern "C" __attribute__((visibility("default"))) int gof_stats_read(unsigned long long* out) {
+extern "C" int gof_stats_read(unsigned long long* out) {
   if (!gof_stats_buffer()) return 0;
   cudaMemcpy(out, g_stats_dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   cudaMemset(g_stats_dev, 0, 8 * sizeof(unsigned long long));
@@ -189,8 +226,7 @@ extern "C" int gof_rasterize_forward(const gof_scene_t* s, gof_alloc_fn geom_all
 
   // rasterizer_impl.cu:334-340: the instance count sizes the binning buffer (one blocking D2H read)
   uint32_t R = 0;
-  GOF_CUDA_OK(cudaMemcpyAsync(&R, geom + GL.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  if ((rc = gof_read_back(&R, geom + GL.total, sizeof(uint32_t), st)) != GOF_OK) return rc;
   *num_rendered = (int)R;
   tr.mark("sync num_rendered");
 
@@ -344,8 +380,7 @@ extern "C" int gof_integrate(const gof_scene_t* s, int PN, const float* points3D
   if ((rc = gof_launch_preprocess(s, v, geom, GL, radii, st)) != GOF_OK) return rc;
   if ((rc = gof_depth_sort_and_offsets(s->P, geom, GL, s->debug != 0, st)) != GOF_OK) return rc;
   uint32_t R = 0;
-  GOF_CUDA_OK(cudaMemcpyAsync(&R, geom + GL.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  if ((rc = gof_read_back(&R, geom + GL.total, sizeof(uint32_t), st)) != GOF_OK) return rc;
   *num_rendered = (int)R;
   const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height);
   char* bin = (char*)binning_alloc(binning_user, BL.bytes);

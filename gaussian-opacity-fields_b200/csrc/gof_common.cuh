@@ -48,6 +48,11 @@ void gof_prof_end(cudaStream_t st);
     gof_prof_end(st);               \
   } while (0)
 
+// Small device->host readbacks (num_rendered, tet-mesh counters) land in a per-thread PINNED slot: a pageable
+// destination turns cudaMemcpyAsync into a staged, driver-synchronised copy.  Returns nullptr if pinning failed.
+void* gof_pinned_slot();   // 64 bytes
+int gof_read_back(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);   // copy + stream sync; GOF_OK / GOF_E_CUDA
+
 // GOF_STATS=1: device counters of the backward blend (pairs visited / evaluated / contributing); nullptr otherwise
 unsigned long long* gof_stats_buffer();
 

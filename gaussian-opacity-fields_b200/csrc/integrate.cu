@@ -110,7 +110,7 @@ __device__ __forceinline__ bool ray_step(const float* v, float op, float rx, flo
   float AA, BB;
   pair_geom_k<K>(v, rx, ry, &AA, &BB);
   const float t = F_DIV(-BB, F_ADD(AA, AA));
-  if ((double)t <= GOF_NEAR_PLANE_D) return false;
+  if (GOF_T_BEHIND_NEAR(t)) return false;
   const double mv = D_FMA((double)F_DIV(-BB, AA), D_MUL((double)BB, 0.25), (double)v[9]);
   float power = (float)D_MUL(mv, -0.5);
   if (power > 0.0f) power = 0.0f;

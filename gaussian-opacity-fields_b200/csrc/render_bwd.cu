@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
         GofPair p;
         float t = 0.f, G = 0.f, alpha = 0.f;
-        double qd = 0.0;
+        double qd = 0.0, rA = 0.0;
         if (contrib) {
           p = gof_pair_geom(v, rx, ry);
           const float bh = 0.5f * p.BB;
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         if (STATS) st_pass += contrib;
         if (contrib) {
           float power;
-          gof_pair_t_power(p, v[9], &t, &power, &qd);
-          if ((double)t <= GOF_NEAR_PLANE_D) contrib = false;
+          gof_pair_t_power(p, v[9], &t, &power, &qd, &rA);
+          if (GOF_T_BEHIND_NEAR(t)) contrib = false;
           else {
             G = F_EXP(power);
             alpha = fminf(F_MUL(q2.z, G), GOF_ALPHA_MAX);
@@ -205,13 +205,15 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         for (int q = 0; q < 16; ++q) g[q] = 0.f;
         if (contrib) {
           // backward.cu:806-817
-          const float mt = gof_mapped_t_fast(t);
-          const float dm_dt = F_DIV(20.0f / 99.8f, t * t);
+          float rt;
+          const float mt = gof_mapped_t_fast(t, &rt);
+          const float dm_dt = ((20.0f / 99.8f) * rt) * rt;   // d/dt of 100/99.8 - (20/99.8)/t
           // IEEE single-precision sqrt and reciprocal (not rsqrt): these feed dL_dview2gaussian, whose chain rule
           // amplifies every ulp by ~1/scale^2
           const float rlen = F_RCP(F_SQRT(F_FMA(p.n2, p.n2, F_FMA(p.n0, p.n0, F_MUL(p.n1, p.n1))) + 1e-7f));
           const float nn0 = -p.n0 * rlen, nn1 = -p.n1 * rlen, nn2 = -p.n2 * rlen;
-          T = T / (1.f - alpha);
+          const float r1a = F_RCP(1.f - alpha);   // alpha <= 0.99
+          T = T * r1a;
           const float w = alpha * T;
           float dL_dalpha = 0.f;
           // colour, :824-837
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
           if (contributor == max_contributor - 1u) dL_dt += ddepth;
           dL_dalpha *= T;
           last_alpha = alpha;
-          dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+          dL_dalpha += (-T_final * r1a) * bg_dot_dpixel;
           // :896-912  2D-mean statistic and opacity
           const float4 b0 = s_recb[j][0], b1 = s_recb[j][1];   // (mx,my,cx,cy) (cz,..)
           const float dx = b0.x - (float)pix_x, dy = b0.y - (float)pix_y;
@@ -257,22 +259,25 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
           // :914-928 in double like the reference; BB/AA = -qd is reused from the forward evaluation
           const float dL_dmin = dL_dG * G * -0.5f;
           g[9] = dL_dmin;   // dL_dC; dL_dopacity = G*dL_dalpha = dL_dC * (-2/opacity) is derived from its sum below
-          const double inv2A = 0.5 / (double)p.AA;
-          const double dL_dA = (double)dL_dmin * qd * qd * 0.25 - (double)dL_dt * qd * inv2A;
-          const double dL_dB = (double)dL_dmin * qd * 0.5 - (double)dL_dt * inv2A;
+          // A and B enter in double like the reference; 1/AA comes from the forward division (rA), -BB/AA = qd.
+          // The sums below are formed by single float FMAs on the rounded dL_dA / dL_dB: one rounding each, like
+          // the reference's double expression stored to float.
+          const double inv2A = 0.5 * rA;
+          const float dA = (float)((double)dL_dmin * qd * qd * 0.25 - (double)dL_dt * qd * inv2A);
+          const float dB2 = (float)((double)dL_dmin * qd - (double)dL_dt * rA);   // 2 * dL_dB
           // :938-952
-          dnrm0 = (float)((double)dnrm0 + dL_dA * rx);
-          dnrm1 = (float)((double)dnrm1 + dL_dA * ry);
-          dnrm2 = (float)((double)dnrm2 + dL_dA);
+          dnrm0 = fmaf(dA, rx, dnrm0);
+          dnrm1 = fmaf(dA, ry, dnrm1);
+          dnrm2 = dnrm2 + dA;
           g[0] = dnrm0 * rx;
           g[1] = dnrm0 * ry + dnrm1 * rx;
           g[2] = dnrm0 + dnrm2 * rx;
           g[3] = dnrm1 * ry;
           g[4] = dnrm1 + dnrm2 * ry;
           g[5] = dnrm2;
-          g[6] = (float)(dL_dB * 2.0 * rx);
-          g[7] = (float)(dL_dB * 2.0 * ry);
-          g[8] = (float)(dL_dB * 2.0);
+          g[6] = dB2 * rx;
+          g[7] = dB2 * ry;
+          g[8] = dB2;
         }
         const float sum = warp_reduce16(g, lane);
         // one red per even lane: 17 global float atomics per (warp, Gaussian) instead of per (pixel, Gaussian)

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
         // ---- exact path: forward.cu:516-541 ----
         float t, power;
         gof_pair_t_power(p, v[9], &t, &power);
-        if ((double)t <= GOF_NEAR_PLANE_D) continue;
+        if (GOF_T_BEHIND_NEAR(t)) continue;
         const float alpha = fminf(F_MUL(q2.z, F_EXP(power)), GOF_ALPHA_MAX);
         if (alpha < GOF_ALPHA_MIN) continue;
         const float test_T = F_MUL(T, F_SUB(1.0f, alpha));

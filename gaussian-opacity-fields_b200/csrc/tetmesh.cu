@@ -211,8 +211,7 @@ int gof_marching_tets_count(int num_verts, const float* sdf, int64_t num_tets, c
   if ((rc = gof_exclusive_scan_u32(f1, f1_off, tmp, &hd->n1, T, false, st)) != GOF_OK) return rc;
   if ((rc = gof_exclusive_scan_u32(f2, f2_off, tmp, &hd->n2, T, false, st)) != GOF_OK) return rc;
   Header h;
-  GOF_CUDA_OK(cudaMemcpyAsync(&h, hd, sizeof(Header), cudaMemcpyDeviceToHost, st));
-  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  { const int rb = gof_read_back(&h, hd, sizeof(Header), st); if (rb != GOF_OK) return rb; }
   *num_faces_out = (int64_t)h.n1 + 2 * (int64_t)h.n2;
   const size_t I = h.n_inst;
   if (I == 0) return GOF_OK;
@@ -245,8 +244,7 @@ int gof_marching_tets_count(int num_verts, const float* sdf, int64_t num_tets, c
   if ((rc = gof_exclusive_scan_u32(head, uid_sorted, tmp, &hd->n_edges, I, false, st)) != GOF_OK) return rc;
   GOF_LAUNCH("tet_uid", st, k_scatter_uid<<<gi, 256, 0, st>>>(I, lo_a, head, uid_sorted, inst_uid));
   GOF_LAUNCH_CHECK(false, st);
-  GOF_CUDA_OK(cudaMemcpyAsync(&h, hd, sizeof(Header), cudaMemcpyDeviceToHost, st));
-  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  { const int rb = gof_read_back(&h, hd, sizeof(Header), st); if (rb != GOF_OK) return rb; }
   *num_edges_out = (int64_t)h.n_edges;
   return GOF_OK;
 }
@@ -267,8 +265,7 @@ int gof_marching_tets_emit(int num_verts, const float* sdf, int64_t num_tets, co
   const TetLayout L = tet_layout(T);
   char* S = (char*)scratch;
   Header h;
-  GOF_CUDA_OK(cudaMemcpyAsync(&h, S + L.header, sizeof(Header), cudaMemcpyDeviceToHost, st));
-  GOF_CUDA_OK(cudaStreamSynchronize(st));
+  { const int rb = gof_read_back(&h, S + L.header, sizeof(Header), st); if (rb != GOF_OK) return rb; }
   if ((int64_t)h.n_edges != num_edges || (int64_t)h.n1 + 2 * (int64_t)h.n2 != num_faces) {
     gof_set_error("marching_tets_emit: sizes do not match the count phase");
     return GOF_E_INVALID;

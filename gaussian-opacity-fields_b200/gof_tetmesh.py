@@ -35,7 +35,7 @@ def _unbatched_marching_tetrahedra(vertices, tets, sdf, scales, chunk_tets=CHUNK
     s = sdf.contiguous().float().reshape(-1)
     sc = scales.contiguous().float().reshape(-1)
     V, T = int(v.shape[0]), int(t.shape[0])
-    scratch = _C._Scratch(dev)
+    scratch = _C._Scratch(dev, "tets")
     nE, nF = ctypes.c_int64(0), ctypes.c_int64(0)
     with torch.cuda.device(dev):
         _C._check(_lib.gof_marching_tets_count(V, s.data_ptr(), T, t.data_ptr() if T else None, chunk_tets, scratch.cb, None,

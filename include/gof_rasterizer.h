@@ -161,6 +161,11 @@ GOF_API unsigned long long gof_launch_count(void);
 GOF_API void gof_profile_enable(int on);
 GOF_API void gof_profile_reset(void);
 GOF_API int gof_profile_report(char* buf, int cap);
+/* "<kernel> <start_ms> <end_ms>" per bracketed launch since the last reset (origin: the first of them): shows idle
+ * gaps between launches.  Returns the bytes needed. */
+GOF_API int gof_profile_timeline(char* buf, int cap);
+/* GOF_STATS=1 only: copies the 8 pair counters of the backward blend to `out` (host) and clears them; 0 if disabled. */
+GOF_API int gof_stats_read(unsigned long long* out);
 
 GOF_API const char* gof_last_error(void);
 GOF_API int gof_version(void);

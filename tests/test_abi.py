@@ -102,3 +102,21 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "gof_oracle" not in text and "oracle/" not in text.replace("the oracle", ""), f"{f} references oracle/"
+
+
+def test_scratch_buffers_die_by_refcount_not_by_gc():
+    """The allocator thunk must not form a reference cycle with the buffer it hands out: the scratch tensor has to
+    be released (to the pool / torch's caching allocator) the moment the caller drops it."""
+    import gc
+    import weakref
+    from diff_gaussian_rasterization import _C
+    gc.disable()
+    try:
+        sc = _C._Scratch(torch.device("cpu"))
+        assert sc.cb(None, 4096) != 0
+        w = weakref.ref(sc.tensor)
+        assert w() is not None and w().numel() == 4096
+        del sc
+        assert w() is None, "scratch tensor kept alive by a reference cycle"
+    finally:
+        gc.enable()

@@ -29,6 +29,10 @@ def test_culling_never_changes_results():
                 np.testing.assert_array_equal(a[k].view(np.int32), b[k].view(np.int32), err_msg=k)
             else:
                 den = max(np.abs(a[k]).max(), 1e-30)
-                err = np.abs(a[k].astype(np.float64) - b[k]).max() / den
-                tol = 0.5 if k.endswith(("dscales", "drot", "dmeans3D")) else 1e-5   # K8 amplifies summation-order noise by ~1/scale^2
-                assert err < tol, f"{k}: {err}"
+                diff = np.abs(a[k].astype(np.float64) - b[k]) / den
+                if k.endswith(("dscales", "drot", "dmeans3D")):
+                    # K8 multiplies the summation-order noise of dv2g (checked to 1e-5 below) by ~1/scale^2, up to 1e5 for
+                    # the needles of scene b: single elements are noise-dominated, so bound the bulk of the distribution
+                    assert np.quantile(diff, 0.99) < 1e-2, f"{k}: q99 {np.quantile(diff, 0.99)}"
+                else:
+                    assert diff.max() < 1e-5, f"{k}: {diff.max()}"
