@@ -56,6 +56,55 @@ int gof_read_back(void* dst, const void* src_dev, size_t bytes, cudaStream_t st)
 // GOF_STATS=1: device counters of the backward blend (pairs visited / evaluated / contributing); nullptr otherwise
 unsigned long long* gof_stats_buffer();
 
+// ---- shared-memory access with an explicit base register ----------------------------------------------
+// On sm_100 a shared address carries the CTA's rank in its cluster; ptxas re-derives that window base
+// (S2UR SR_CgaCtaId + UMOV + ULEA) next to every dynamically indexed access when registers are tight, which was
+// 5-8 issue slots per visited Gaussian in the blend kernels.  gof_smem_base() turns the base into an opaque
+// register value once; gof_lds* then compile to a bare LDS [R + imm].
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t gof_smem_base(const void* p) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));
+  return a;
+}
+template <int OFF>
+__device__ __forceinline__ float4 gof_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float2 gof_lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float gof_lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+// 1/x, <= 1 ulp, no range guard (MUFU.RCP): for x known to be a normal number, or where inf/NaN are acceptable
+__device__ __forceinline__ float gof_rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 1/x refined by one Newton step (error < 1 ulp for normal x)
+__device__ __forceinline__ float gof_rcp_newton(float x) {
+  const float r = gof_rcp_approx(x);
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+// 1/sqrt(x) refined by one Newton step (error ~1 ulp, like an IEEE sqrt followed by an IEEE reciprocal)
+__device__ __forceinline__ float gof_rsqrt_newton(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  const float e = fmaf(-x * y, y, 1.0f);
+  return fmaf(0.5f * y, e, y);
+}
+#endif
+
 // ---- per-Gaussian records ---------------------------------------------------------------------
 // One 64-byte, 64-byte-aligned record per Gaussian holds everything the forward blend gathers per
 // (tile,Gaussian) instance: two 32-byte sectors instead of the reference's three unaligned gathers

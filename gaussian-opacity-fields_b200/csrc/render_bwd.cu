@@ -73,11 +73,11 @@ __device__ __forceinline__ float warp_reduce16(const float (&a)[16], int lane) {
 template <bool STATS, int MINB>
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const BwdArgs a) {
   unsigned long long st_visit = 0, st_eval = 0, st_pass = 0, st_contrib = 0, st_anyhit = 0;
-  __shared__ float4 s_rec[BATCH][4];
-  __shared__ float4 s_recb[BATCH][2];
-  __shared__ float s_thr[BATCH];
-  __shared__ uint32_t s_id[BATCH];
+  // 28 KB: rows of 112 bytes per staged Gaussian = GofSplat (64 B) | GofSplatBwd (32 B) | (thr, id, -, -); one row base
+  // register serves every load of a visit (see gof_smem_base)
+  __shared__ float4 s_rec[BATCH][7];
   __shared__ uint32_t s_max;
+  const uint32_t s_base = gof_smem_base(&s_rec[0][0]);
 
   const int tile = blockIdx.x;
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
@@ -141,14 +141,14 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
     const int progress = i * BATCH + (int)threadIdx.x;
     if (progress < used) {
       const uint32_t g = a.point_list[range.x + (uint32_t)(used - 1 - progress)];
-      s_id[threadIdx.x] = g;
       const float4* src = reinterpret_cast<const float4*>(a.splat + g);
       const float4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
       s_rec[threadIdx.x][0] = r0; s_rec[threadIdx.x][1] = r1; s_rec[threadIdx.x][2] = r2; s_rec[threadIdx.x][3] = r3;
       const float4* srcb = reinterpret_cast<const float4*>(a.splat_bwd + g);
-      s_recb[threadIdx.x][0] = __ldg(srcb); s_recb[threadIdx.x][1] = __ldg(srcb + 1);
+      s_rec[threadIdx.x][4] = __ldg(srcb); s_rec[threadIdx.x][5] = __ldg(srcb + 1);
       const float op = r2.z;
-      s_thr[threadIdx.x] = (op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
+      s_rec[threadIdx.x][6] = make_float4((op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000),
+                                          __uint_as_float(g), 0.f, 0.f);
     }
     __syncthreads();
 
@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         bool contrib = inside && contributor < last_contributor;
         if (STATS) { st_visit += (lane == 0); st_eval += contrib; }
 
-        const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
+        const uint32_t row = s_base + (uint32_t)j * 112u;
+        const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
         const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
         GofPair p;
         float t = 0.f, G = 0.f, alpha = 0.f;
@@ -180,10 +181,10 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         if (contrib) {
           p = gof_pair_geom(v, rx, ry);
           const float bh = 0.5f * p.BB;
-          const float qf = bh * bh * __frcp_rn(p.AA);
+          const float qf = bh * bh * gof_rcp_approx(p.AA);   // error bound: see render_fwd.cu
           const float pw = -0.5f * (v[9] - qf);
-          const float bound = fmaf(fabsf(qf), 3e-7f, pw);
-          if (bound < s_thr[j] && fabsf(p.AA) < 1e30f) contrib = false;
+          const float bound = fmaf(fabsf(qf), 3.5e-7f, pw);
+          if (bound < gof_lds32<96>(row) && fabsf(p.AA) < 1e30f) contrib = false;
         }
         if (STATS) st_pass += contrib;
         if (contrib) {
@@ -208,16 +209,16 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
           float rt;
           const float mt = gof_mapped_t_fast(t, &rt);
           const float dm_dt = ((20.0f / 99.8f) * rt) * rt;   // d/dt of 100/99.8 - (20/99.8)/t
-          // IEEE single-precision sqrt and reciprocal (not rsqrt): these feed dL_dview2gaussian, whose chain rule
-          // amplifies every ulp by ~1/scale^2
-          const float rlen = F_RCP(F_SQRT(F_FMA(p.n2, p.n2, F_FMA(p.n0, p.n0, F_MUL(p.n1, p.n1))) + 1e-7f));
+          // 1/|n| to ~1 ulp (Newton-refined rsqrt; as accurate as an IEEE sqrt followed by an IEEE reciprocal -- the
+          // plain 2-ulp rsqrt is not: this feeds dL_dview2gaussian, whose chain rule amplifies every ulp by ~1/scale^2)
+          const float rlen = gof_rsqrt_newton(F_FMA(p.n2, p.n2, F_FMA(p.n0, p.n0, F_MUL(p.n1, p.n1))) + 1e-7f);
           const float nn0 = -p.n0 * rlen, nn1 = -p.n1 * rlen, nn2 = -p.n2 * rlen;
-          const float r1a = F_RCP(1.f - alpha);   // alpha <= 0.99
+          const float r1a = gof_rcp_newton(1.f - alpha);   // 1 - alpha in [0.01, 1]
           T = T * r1a;
           const float w = alpha * T;
           float dL_dalpha = 0.f;
           // colour, :824-837
-          const float4 q3 = s_rec[j][3];
+          const float2 q3 = gof_lds64<48>(row);
           const float c0 = q2.w, c1 = q3.x, c2 = q3.y;
           acc_c0 = last_alpha * last_c0 + (1.f - last_alpha) * acc_c0; last_c0 = c0;
           acc_c1 = last_alpha * last_c1 + (1.f - last_alpha) * acc_c1; last_c1 = c1;
@@ -247,12 +248,13 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
           last_alpha = alpha;
           dL_dalpha += (-T_final * r1a) * bg_dot_dpixel;
           // :896-912  2D-mean statistic and opacity
-          const float4 b0 = s_recb[j][0], b1 = s_recb[j][1];   // (mx,my,cx,cy) (cz,..)
+          const float4 b0 = gof_lds128<64>(row);   // (mx, my, cx, cy)
+          const float b1x = gof_lds32<80>(row);    // cz
           const float dx = b0.x - (float)pix_x, dy = b0.y - (float)pix_y;
           const float dL_dG = q2.z * dL_dalpha;
           const float gdx = G * dx, gdy = G * dy;
           const float dG_ddelx = -gdx * b0.z - gdy * b0.w;
-          const float dG_ddely = -gdy * b1.x - gdx * b0.w;
+          const float dG_ddely = -gdy * b1x - gdx * b0.w;
           g[13] = dL_dG * dG_ddelx * ddelx_dx;
           g[14] = dL_dG * dG_ddely * ddely_dy;
           g[15] = fabsf(g[13]) + fabsf(g[14]);
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         }
         const float sum = warp_reduce16(g, lane);
         // one red per even lane: 17 global float atomics per (warp, Gaussian) instead of per (pixel, Gaussian)
-        const uint32_t gid = s_id[j];
+        const uint32_t gid = __float_as_uint(gof_lds32<100>(row));
         if (!(lane & 1) && sum != 0.f) {
           float* dst;
           if (vidx < 10) dst = a.dL_dv2g + 10 * (size_t)gid + vidx;

@@ -44,8 +44,10 @@ __device__ __forceinline__ bool box_hits(uint32_t lo, uint32_t hi, int wx0, int 
 
 template <int MINB>
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const FwdArgs a) {
-  __shared__ float4 s_rec[BATCH][4];   // 16 KB: the 64-byte records of the current batch
-  __shared__ float s_thr[BATCH];       // -ln(255*opacity): the largest power that can still be rejected
+  // 20 KB: rows of 80 bytes = the 64-byte record of a staged Gaussian + (thr, -, -, -), thr = -ln(255*opacity): the
+  // largest power that can still be rejected.  One row base serves every load of a visit.
+  __shared__ float4 s_rec[BATCH][5];
+  const uint32_t s_base = gof_smem_base(&s_rec[0][0]);
 
   const int tile = blockIdx.x;
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
     {
       const float op = nx2.z;   // (v2g[8], v2g[9], opacity, rgb0)
       // alpha = op*exp(power) < 1/255  <=>  power < -ln(255*op);   op <= 0 can never contribute
-      s_thr[threadIdx.x] = (op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
+      s_rec[threadIdx.x][4].x = (op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
     }
     __syncthreads();
     // issue the gather for the next batch; it completes while this batch is blended
@@ -116,17 +118,20 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
         m &= m - 1;
         if (done) continue;
         const uint32_t contributor = (uint32_t)(i * BATCH + j + 1);   // 1-based position in the tile list
-        const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
+        const uint32_t row = s_base + (uint32_t)j * 80u;
+        const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
         const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
         const GofPair p = gof_pair_geom(v, rx, ry);
 
         // ---- conservative reject (single precision, error-bounded) ----
         {
           const float bh = 0.5f * p.BB;
-          const float qf = bh * bh * __frcp_rn(p.AA);           // ~ BB^2/(4AA), rel. error < 3e-7
+          // ~ BB^2/(4AA): bh*bh (1/2 ulp), MUFU.RCP (1 ulp, AA denormal -> inf -> not rejected), product (1/2 ulp):
+          // relative error <= 2.4e-7 < 3.5e-7
+          const float qf = bh * bh * gof_rcp_approx(p.AA);
           const float pw = -0.5f * (v[9] - qf);                  // approximate power
-          const float bound = fmaf(fabsf(qf), 3e-7f, pw);        // pw + |error|
-          if (bound < s_thr[j] && fabsf(p.AA) < 1e30f) continue;
+          const float bound = fmaf(fabsf(qf), 3.5e-7f, pw);      // pw + |error|
+          if (bound < gof_lds32<64>(row) && fabsf(p.AA) < 1e30f) continue;
         }
 
         // ---- exact path: forward.cu:516-541 ----
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
         distortion = F_FMA(T, F_MUL(err, alpha), distortion);
         dist1 = F_FMA(T, F_MUL(alpha, mt), dist1);
         dist2 = F_FMA(T, F_MUL(m2, alpha), dist2);
-        const float4 q3 = s_rec[j][3];
+        const float2 q3 = gof_lds64<48>(row);   // rgb1, rgb2
         C0 = F_FMA(T, F_MUL(alpha, q2.w), C0);
         C1 = F_FMA(T, F_MUL(alpha, q3.x), C1);
         C2 = F_FMA(T, F_MUL(alpha, q3.y), C2);

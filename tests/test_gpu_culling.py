@@ -13,17 +13,20 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(cull, path):
+def _run(cull, inputs, path):
     env = dict(os.environ, GOF_CULL=cull)
     env["PYTHONPATH"] = os.pathsep.join([HERE, os.path.join(HERE, "..", "gaussian-opacity-fields_b200"), env.get("PYTHONPATH", "")])
-    subprocess.check_call([sys.executable, os.path.join(HERE, "_cull_probe.py"), path], env=env)
+    subprocess.check_call([sys.executable, os.path.join(HERE, "_cull_probe.py"), inputs, path], env=env)
     return np.load(path)
 
 
 def test_culling_never_changes_results():
+    import _cull_probe
     with tempfile.TemporaryDirectory() as d:
-        a = _run("0", os.path.join(d, "a.npz"))
-        b = _run("1", os.path.join(d, "b.npz"))
+        inputs = os.path.join(d, "inputs.npz")
+        _cull_probe.make_inputs(inputs)      # once: both modes must see bit-identical Gaussians
+        a = _run("0", inputs, os.path.join(d, "a.npz"))
+        b = _run("1", inputs, os.path.join(d, "b.npz"))
         for k in a.files:
             if k.endswith(("_color", "_ncontrib", "_accum")):
                 np.testing.assert_array_equal(a[k].view(np.int32), b[k].view(np.int32), err_msg=k)
