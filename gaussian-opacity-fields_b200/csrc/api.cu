@@ -242,7 +242,7 @@ extern "C" int gof_rasterize_forward(const gof_scene_t* s, gof_alloc_fn geom_all
 }
 
 extern "C" int gof_rasterize_backward(const gof_scene_t* s, int num_rendered, const int* radii,
-                                      const void* geom_buffer, const void* binning_buffer,
+                                      void* geom_buffer, const void* binning_buffer,
                                       const void* image_buffer, const float* dL_dpix, float* dL_dmean2D,
                                       float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
                                       float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
@@ -266,12 +266,14 @@ extern "C" int gof_rasterize_backward(const gof_scene_t* s, int num_rendered, co
   const GofGeomLayout GL = gof_geom_layout((size_t)s->P);
   const GofImageLayout IL = gof_image_layout(s->width, s->height);
   const GofBinLayout BL = gof_bin_layout((size_t)num_rendered, s->width, s->height);
-  if ((rc = gof_launch_render_backward(s, v, (const char*)geom_buffer, GL, (const char*)binning_buffer, BL,
-                                       (const char*)image_buffer, IL, dL_dpix, dL_dmean2D, dL_dopacity, dL_dcolor,
-                                       dL_dview2gaussian, st)) != GOF_OK)
+  // The geometry buffer is the caller's scratch for this view: its last section holds the blend kernel's 64-byte
+  // per-Gaussian accumulator rows, zeroed and filled by every backward call (the forward state in it is only read).
+  char* geom = static_cast<char*>(geom_buffer);
+  if ((rc = gof_launch_render_backward(s, v, geom, GL, (const char*)binning_buffer, BL, (const char*)image_buffer, IL, dL_dpix,
+                                       st)) != GOF_OK)
     return rc;
-  return gof_launch_preprocess_backward(s, v, (const char*)geom_buffer, GL, radii, dL_dcolor, dL_dview2gaussian,
-                                        dL_dmean3D, dL_dsh, dL_dscale, dL_drot, st);
+  return gof_launch_preprocess_backward(s, v, geom, GL, radii, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dview2gaussian, dL_dmean3D,
+                                        dL_dsh, dL_dscale, dL_drot, st);
 }
 
 extern "C" int gof_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

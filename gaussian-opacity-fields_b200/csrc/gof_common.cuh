@@ -142,6 +142,7 @@ struct GofGeomLayout {      // "geomBuffer": everything sized by P
   size_t hist;                         // radix block histograms [RADIX][blocks]
   size_t scan_tmp;                     // scan block sums
   size_t total;                        // u32 num_rendered (device copy)
+  size_t grad_acc;                     // float[P][16]: backward accumulators of the blend kernel (dv2g[10], dcolor[3], dmean2D[3])
   size_t bytes;
 };
 
@@ -163,6 +164,7 @@ static inline GofGeomLayout gof_geom_layout(size_t P) {
   L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(P) + 1) * 4);
   L.scan_tmp = take((P / 1024 + 2) * 4 + 4096);
   L.total = take(256);
+  L.grad_acc = take(P * 64);
   L.bytes = o;
   return L;
 }
@@ -250,8 +252,8 @@ static inline GofView gof_make_view(const gof_scene_t* s) {
 int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, const GofGeomLayout& L,
                           int* radii, cudaStream_t st);
 int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const char* geom,
-                                   const GofGeomLayout& L, const int* radii, const float* dL_dcolor,
-                                   const float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
+                                   const GofGeomLayout& L, const int* radii, float* dL_dmean2D, float* dL_dopacity,
+                                   float* dL_dcolor, float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
                                    float* dL_drot, cudaStream_t st);
 int gof_launch_mark_visible(int P, const float* means3D, const float* vm, unsigned char* present,
                             cudaStream_t st);
@@ -296,8 +298,6 @@ int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const f
 int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char* geom,
                               const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL, char* img,
                               const GofImageLayout& IL, float* out_color, cudaStream_t st);
-int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, const char* geom,
+int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geom,
                                const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL,
-                               const char* img, const GofImageLayout& IL, const float* dL_dpix,
-                               float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor, float* dL_dv2g,
-                               cudaStream_t st);
+                               const char* img, const GofImageLayout& IL, const float* dL_dpix, cudaStream_t st);

@@ -203,8 +203,12 @@ struct PreBwdArgs {
   const float* rotations;
   const float* viewmatrix;
   const float* cam_pos;
-  const float* dL_dcolor;
-  const float* dL_dv2g;
+  const float4* grad_acc;   // [P][4] float4: the blend kernel's accumulator rows (dv2g[10] | dcolor[3] | dmean2D[3])
+  const GofSplat* splat;    // for the effective opacity (dL_dopacity = -2/opacity * dL_dC)
+  float* dL_dmean2D;        // outputs unpacked from the accumulator row
+  float* dL_dopacity;
+  float* dL_dcolor;
+  float* dL_dv2g;
   float* dL_dmean3D;
   float* dL_dsh;
   float* dL_dscale;
@@ -238,6 +242,24 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.P || !(a.radii[idx] > 0)) return;
 
+  // the blend kernel's 64-byte accumulator row -> the public gradient tensors
+  const float4 g0 = a.grad_acc[4 * (size_t)idx], g1 = a.grad_acc[4 * (size_t)idx + 1], g2 = a.grad_acc[4 * (size_t)idx + 2],
+               g3 = a.grad_acc[4 * (size_t)idx + 3];
+  const float accv[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
+  {
+    float* dv = a.dL_dv2g + 10 * (size_t)idx;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) dv[k] = accv[k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a.dL_dcolor[3 * (size_t)idx + c] = accv[10 + c];
+      a.dL_dmean2D[3 * (size_t)idx + c] = accv[13 + c];
+    }
+    // alpha = opacity * G, dL_dC = dL_dG * G * -1/2  =>  sum(G * dL_dalpha) = -2/opacity * sum(dL_dC)   (backward.cu:912)
+    const float op = a.splat[idx].opacity;
+    a.dL_dopacity[idx] = (accv[9] != 0.f) ? accv[9] * (-2.0f / op) : 0.f;
+  }
+
   const float mx = a.means3D[3 * idx], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
   float dmean[3] = {0.f, 0.f, 0.f};
 
@@ -249,10 +271,9 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
     const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
     const double r = q.x, x = q.y, y = q.z, z = q.w;
     const double sx = a.scales[3 * idx], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
-    const float* dvf = a.dL_dv2g + 10 * (size_t)idx;
     double dv[10];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) dv[k] = (double)dvf[k];
+    for (int k = 0; k < 10; ++k) dv[k] = (double)accv[k];
 
     M3 R;   // glm::mat3 R(...), column-major constructor
     R.m[0][0] = 1. - 2. * (y * y + z * z); R.m[0][1] = 2. * (x * y - r * z); R.m[0][2] = 2. * (x * z + r * y);
@@ -359,7 +380,7 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
     const unsigned char cb = a.clamped[idx];
     float dRGB[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) dRGB[c] = a.dL_dcolor[3 * idx + c] * ((cb >> c) & 1 ? 0.f : 1.f);
+    for (int c = 0; c < 3; ++c) dRGB[c] = accv[10 + c] * ((cb >> c) & 1 ? 0.f : 1.f);
 
     float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
 #define SH(k, c) sh[3 * (k) + (c)]
@@ -469,8 +490,8 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
 }
 
 int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const char* geom,
-                                   const GofGeomLayout& L, const int* radii, const float* dL_dcolor,
-                                   const float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
+                                   const GofGeomLayout& L, const int* radii, float* dL_dmean2D, float* dL_dopacity,
+                                   float* dL_dcolor, float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
                                    float* dL_drot, cudaStream_t st) {
   (void)v;
   PreBwdArgs a;
@@ -478,6 +499,9 @@ int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const
   a.means3D = s->means3D; a.radii = radii; a.shs = s->shs;
   a.clamped = reinterpret_cast<const unsigned char*>(geom + L.clamped);
   a.scales = s->scales; a.rotations = s->rotations; a.viewmatrix = s->viewmatrix; a.cam_pos = s->cam_pos;
+  a.grad_acc = reinterpret_cast<const float4*>(geom + L.grad_acc);
+  a.splat = reinterpret_cast<const GofSplat*>(geom + L.splat);
+  a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity;
   a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g; a.dL_dmean3D = dL_dmean3D; a.dL_dsh = dL_dsh;
   a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
   GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + 255) / 256, 256, 0, st>>>(a));

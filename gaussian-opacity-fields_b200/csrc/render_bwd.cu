@@ -26,10 +26,7 @@ struct BwdArgs {
   const uint32_t* ncontrib;  // [2][tiles*256]
   const float* dL_dpix;      // [9][H][W]
   size_t plane;
-  float* dL_dmean2D;   // [P,3]
-  float* dL_dopacity;  // [P]
-  float* dL_dcolor;    // [P,3]
-  float* dL_dv2g;      // [P,10]
+  float* grad_acc;     // [P][16]: dL_dview2gaussian[10] | dL_dcolor[3] | dL_dmean2D[3] (64-byte rows, zeroed per call)
   unsigned long long* stats;   // optional [8] counters (GOF_STATS=1), else nullptr
 };
 
@@ -282,16 +279,10 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
           g[8] = dB2;
         }
         const float sum = warp_reduce16(g, lane);
-        // one red per even lane: 17 global float atomics per (warp, Gaussian) instead of per (pixel, Gaussian)
+        // one red per even lane into the Gaussian's 64-byte accumulator row: 16 global float atomics per (warp, Gaussian)
+        // instead of 17 per (pixel, Gaussian); dL_dopacity = -2/opacity * sum(dL_dC) is formed by k_preprocess_backward
         const uint32_t gid = __float_as_uint(gof_lds32<100>(row));
-        if (!(lane & 1) && sum != 0.f) {
-          float* dst;
-          if (vidx < 10) dst = a.dL_dv2g + 10 * (size_t)gid + vidx;
-          else if (vidx < 13) dst = a.dL_dcolor + 3 * (size_t)gid + (vidx - 10);
-          else dst = a.dL_dmean2D + 3 * (size_t)gid + (vidx - 13);
-          atomicAdd(dst, sum);
-          if (vidx == 9) atomicAdd(a.dL_dopacity + gid, sum * (-2.0f / q2.z));   // alpha >= 1/255 implies opacity > 0
-        }
+        if (!(lane & 1) && sum != 0.f) atomicAdd(a.grad_acc + ((size_t)gid * 16 + vidx), sum);
       }
     }
   }
@@ -304,10 +295,9 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
 
 }  // namespace
 
-int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, const char* geom, const GofGeomLayout& GL,
+int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geom, const GofGeomLayout& GL,
                                const char* bin, const GofBinLayout& BL, const char* img, const GofImageLayout& IL,
-                               const float* dL_dpix, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
-                               float* dL_dv2g, cudaStream_t st) {
+                               const float* dL_dpix, cudaStream_t st) {
   BwdArgs a;
   a.W = v.W; a.H = v.H; a.grid_x = v.grid_x; a.focal_x = v.focal_x; a.focal_y = v.focal_y;
   a.ranges = reinterpret_cast<const uint2*>(img + IL.ranges);
@@ -319,7 +309,8 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, const cha
   a.ncontrib = reinterpret_cast<const uint32_t*>(img + IL.ncontrib);
   a.dL_dpix = dL_dpix;
   a.plane = (size_t)v.tiles * 256;
-  a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g;
+  a.grad_acc = reinterpret_cast<float*>(geom + GL.grad_acc);
+  GOF_CUDA_OK(cudaMemsetAsync(a.grad_acc, 0, (size_t)s->P * 64, st));
   a.stats = gof_stats_buffer();
   static int occ = -1;   // GOF_BWD_OCC=2|3|4 (tuning knob)
   if (occ < 0) { const char* e = getenv("GOF_BWD_OCC"); occ = e ? atoi(e) : 4; }

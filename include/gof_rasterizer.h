@@ -84,9 +84,11 @@ GOF_API int gof_rasterize_forward(const gof_scene_t* scene,
 /* Rasterizer::backward (rasterizer_impl.cu:409-526) == _C.rasterize_gaussians_backward.
  * All dL_d* outputs must be zero-initialised by the caller (rasterize_points.cu:161-170).
  * dL_dconic [P,4] and dL_dcov3D [P,6] are accepted and left untouched (the reference's EWA backward
- * is disabled, backward.cu:991-1007, 627-630).  dL_dsh may be NULL when M == 0. */
+ * is disabled, backward.cu:991-1007, 627-630).  dL_dsh may be NULL when M == 0.
+ * geom_buffer is the forward's geometry scratch: the backward reads the forward state in it and uses its last
+ * section (64 bytes per Gaussian) as accumulator rows, re-zeroed by every call -- hence not const. */
 GOF_API int gof_rasterize_backward(const gof_scene_t* scene, int num_rendered, const int* radii,
-                           const void* geom_buffer, const void* binning_buffer, const void* image_buffer,
+                           void* geom_buffer, const void* binning_buffer, const void* image_buffer,
                            const float* dL_dpix,        /* [9,H,W] */
                            float* dL_dmean2D,           /* [P,3] */
                            float* dL_dconic,            /* [P,4]  untouched */
