@@ -105,10 +105,19 @@ __device__ __forceinline__ void pair_geom_k(const float* v, float rx, float ry, 
 // one ray of pass 1 (forward.cu:931-975): true when the Gaussian is blended on this ray; then *alpha / *test_T hold the
 // blend weight and the transmittance after it, and tmax has been raised to t (forward.cu:965-967)
 template <int K>
-__device__ __forceinline__ bool ray_step(const float* v, float op, float rx, float ry, float Tk, float& tmax, float* alpha,
-                                         float* test_T) {
+__device__ __forceinline__ bool ray_step(const float* v, float op, float thr, float rx, float ry, float Tk, float& tmax,
+                                         float* alpha, float* test_T) {
   float AA, BB;
   pair_geom_k<K>(v, rx, ry, &AA, &BB);
+  {
+    // conservative single-precision reject of alpha < 1/255 (both early-outs below return false as well): the exact
+    // power is -1/2 (CC - q) with q = fl32(-BB/AA) * BB/4 = BB^2/(4AA) (1 +- 6e-8); qf below carries <= 2.4e-7 (see
+    // render_fwd.cu), thr = -ln(255 op) - 2e-3 absorbs the remaining roundings
+    const float bh = 0.5f * BB;
+    const float qf = bh * bh * gof_rcp_approx(AA);
+    const float pw = -0.5f * (v[9] - qf);
+    if (fmaf(fabsf(qf), 5e-7f, pw) < thr && fabsf(AA) < 1e30f) return false;
+  }
   const float t = F_DIV(-BB, F_ADD(AA, AA));
   if (GOF_T_BEHIND_NEAR(t)) return false;
   const double mv = D_FMA((double)F_DIV(-BB, AA), D_MUL((double)BB, 0.25), (double)v[9]);
@@ -125,11 +134,12 @@ __device__ __forceinline__ bool ray_step(const float* v, float op, float rx, flo
 }
 
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE, 3) k_integrate(const IntArgs a) {
-  __shared__ float4 s_rec[BATCH][4];
+  __shared__ float4 s_rec[BATCH][5];   // 80-byte rows: GofSplat | (thr, -, -, -), see render_fwd.cu
   __shared__ uint32_t s_cnt[256];      // contributors recorded per pixel (slot = thread of that pixel)
   __shared__ float s_col[256][3];      // pixel colour (C + T*bg)
   __shared__ uint32_t s_proj[256];     // points that fell into each pixel
 
+  const uint32_t s_base = gof_smem_base(&s_rec[0][0]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint16_t* slab = a.ids + (size_t)blockIdx.x * 256 * GOF_INT_MAX_CONTRIB;
   uint16_t* my_ids = slab + (size_t)threadIdx.x * GOF_INT_MAX_CONTRIB;
@@ -167,8 +177,11 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, 3) k_integrate(const IntArgs a
       if (progress < total) {
         const uint32_t g = a.point_list[range.x + progress];
         const float4* src = reinterpret_cast<const float4*>(a.splat + g);
+        const float4 r2 = __ldg(src + 2);
         s_rec[threadIdx.x][0] = __ldg(src); s_rec[threadIdx.x][1] = __ldg(src + 1);
-        s_rec[threadIdx.x][2] = __ldg(src + 2); s_rec[threadIdx.x][3] = __ldg(src + 3);
+        s_rec[threadIdx.x][2] = r2; s_rec[threadIdx.x][3] = __ldg(src + 3);
+        const float op = r2.z;
+        s_rec[threadIdx.x][4].x = (op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
       }
       __syncthreads();
       const int nb = min(BATCH, total - i * BATCH);
@@ -184,23 +197,25 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, 3) k_integrate(const IntArgs a
           m &= m - 1;
           if (done) continue;
           const uint32_t contributor = (uint32_t)(i * BATCH + j + 1);
-          const float4 q0 = s_rec[j][0], q1 = s_rec[j][1], q2 = s_rec[j][2];
+          const uint32_t row = s_base + (uint32_t)j * 80u;
+          const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
           const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
           const float op = q2.z;
+          const float thr = gof_lds32<64>(row);
           float al, tt;
           bool used = false;
-          if (ray_step<0>(v, op, rx0, ry0, T0, tmax, &al, &tt)) {
-            const float4 q3 = s_rec[j][3];
+          if (ray_step<0>(v, op, thr, rx0, ry0, T0, tmax, &al, &tt)) {
+            const float2 q3 = gof_lds64<48>(row);
             C0 = F_FMA(T0, F_MUL(al, q2.w), C0);
             C1 = F_FMA(T0, F_MUL(al, q3.x), C1);
             C2 = F_FMA(T0, F_MUL(al, q3.y), C2);
             Aacc = F_FMA(T0, al, Aacc);
             T0 = tt; used = true;
           }
-          if (ray_step<1>(v, op, rxm, rym, T1, tmax, &al, &tt)) { T1 = tt; used = true; }
-          if (ray_step<2>(v, op, rxp, rym, T2, tmax, &al, &tt)) { T2 = tt; used = true; }
-          if (ray_step<3>(v, op, rxm, ryp, T3, tmax, &al, &tt)) { T3 = tt; used = true; }
-          if (ray_step<4>(v, op, rxp, ryp, T4, tmax, &al, &tt)) { T4 = tt; used = true; }
+          if (ray_step<1>(v, op, thr, rxm, rym, T1, tmax, &al, &tt)) { T1 = tt; used = true; }
+          if (ray_step<2>(v, op, thr, rxp, rym, T2, tmax, &al, &tt)) { T2 = tt; used = true; }
+          if (ray_step<3>(v, op, thr, rxm, ryp, T3, tmax, &al, &tt)) { T3 = tt; used = true; }
+          if (ray_step<4>(v, op, thr, rxp, ryp, T4, tmax, &al, &tt)) { T4 = tt; used = true; }
           if (used) {
             last_contributor = contributor;
             my_ids[n_local] = (uint16_t)contributor;    // uint16 truncation as in forward.cu:983
