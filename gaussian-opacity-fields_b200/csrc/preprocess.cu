@@ -238,10 +238,22 @@ __device__ __forceinline__ M3 m3_t(const M3& A) {
   return o;
 }
 
-__global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P || !(a.radii[idx] > 0)) return;
+constexpr int K8_THREADS = 128;
+constexpr int K8_ROW = 49;   // 48 SH-gradient floats per Gaussian + 1 pad: lanes of a warp hit distinct banks
 
+__global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwdArgs a) {
+  // dL_dsh leaves through shared memory: a thread produces its Gaussian's 3*M floats one coefficient at a time (stride-192-byte
+  // scalar stores: ncu showed the kernel waiting on the LSU queue, lg_throttle 14 / long_scoreboard 17 warps per issue), the
+  // warp then writes its 32 consecutive Gaussians as one contiguous block with 128-bit stores.
+  __shared__ float s_dsh[K8_THREADS / 32][32 * K8_ROW];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool active = idx < a.P && a.radii[idx] > 0;
+  const unsigned active_mask = __ballot_sync(0xffffffffu, active);
+  if (active_mask == 0u) return;   // whole warp invisible
+  float* my_dsh = &s_dsh[warp][lane * K8_ROW];
+
+  if (active) {
   // the blend kernel's 64-byte accumulator row -> the public gradient tensors
   const float4 g0 = a.grad_acc[4 * (size_t)idx], g1 = a.grad_acc[4 * (size_t)idx + 1], g2 = a.grad_acc[4 * (size_t)idx + 2],
                g3 = a.grad_acc[4 * (size_t)idx + 3];
@@ -375,8 +387,20 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
     const float dox = mx - a.cam_pos[0], doy = my - a.cam_pos[1], doz = mz - a.cam_pos[2];
     const float len = sqrtf(dox * dox + doy * doy + doz * doz);
     const float x = dox / len, y = doy / len, z = doz / len;
-    const float* sh = a.shs + (size_t)idx * a.M * 3;
-    float* dsh = a.dL_dsh + (size_t)idx * a.M * 3;
+    float sh[48];
+    if (a.M == 16) {   // 192-byte rows: 12 x LDG.128
+      const float4* src = reinterpret_cast<const float4*>(a.shs + (size_t)idx * 48);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const float4 t4 = __ldg(src + k);
+        sh[4 * k] = t4.x; sh[4 * k + 1] = t4.y; sh[4 * k + 2] = t4.z; sh[4 * k + 3] = t4.w;
+      }
+    } else {
+      const float* src = a.shs + (size_t)idx * a.M * 3;
+#pragma unroll
+      for (int k = 0; k < 48; ++k) sh[k] = (k < 3 * a.M) ? src[k] : 0.f;
+    }
+    float* dsh = my_dsh;
     const unsigned char cb = a.clamped[idx];
     float dRGB[3];
 #pragma unroll
@@ -456,6 +480,30 @@ __global__ void __launch_bounds__(256) k_preprocess_backward(const PreBwdArgs a)
   a.dL_dmean3D[3 * idx + 0] = dmean[0];
   a.dL_dmean3D[3 * idx + 1] = dmean[1];
   a.dL_dmean3D[3 * idx + 2] = dmean[2];
+  }   // active
+
+  // ---- the warp's dL_dsh rows: shared memory -> global, contiguous ----
+  if (a.shs != nullptr) {
+    __syncwarp();
+    const int nw = 3 * (a.D + 1) * (a.D + 1);             // floats written per Gaussian (backward.cu writes degree <= D only)
+    const size_t g0 = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32;   // first Gaussian of this warp
+    if (a.M == 16 && nw == 48) {
+      float4* dst = reinterpret_cast<float4*>(a.dL_dsh + g0 * 48);
+#pragma unroll 4
+      for (int i = lane; i < 32 * 12; i += 32) {
+        const int g = i / 12, j = (i - g * 12) * 4;
+        if ((active_mask >> g) & 1u) {
+          const float* r = &s_dsh[warp][g * K8_ROW + j];
+          dst[i] = make_float4(r[0], r[1], r[2], r[3]);
+        }
+      }
+    } else {
+      for (int i = lane; i < 32 * nw; i += 32) {
+        const int g = i / nw, j = i - g * nw;
+        if ((active_mask >> g) & 1u) a.dL_dsh[(g0 + g) * (size_t)a.M * 3 + j] = s_dsh[warp][g * K8_ROW + j];
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -504,7 +552,7 @@ int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const
   a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity;
   a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g; a.dL_dmean3D = dL_dmean3D; a.dL_dsh = dL_dsh;
   a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
-  GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + 255) / 256, 256, 0, st>>>(a));
+  GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + K8_THREADS - 1) / K8_THREADS, K8_THREADS, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }
