@@ -197,6 +197,9 @@ struct GofBinLayout {       // "binningBuffer": everything sized by R = num_rend
   int bits[4];              // digit widths, low digit first
   size_t point_list;        // offset of the final sorted Gaussian-id list (val_a or val_b)
   size_t sorted_keys;       // offset of the final sorted tile-id list
+  size_t vmask_R;           // = R
+  size_t vmask;             // u32[8][R]: for warp w of the tile and list entry r, the lanes (pixels) that blended it in
+                            // the forward; written by k_render_forward, the backward visits exactly those
   size_t bytes;
 };
 
@@ -228,6 +231,8 @@ static inline GofBinLayout gof_bin_layout(size_t R, int W, int H) {
   L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(R) + 1) * 4);
   L.point_list = (L.passes % 2 == 0) ? L.val_a : L.val_b;
   L.sorted_keys = (L.passes % 2 == 0) ? L.key_a : L.key_b;
+  L.vmask_R = R;
+  L.vmask = take(R * 32);
   L.bytes = o;
   return L;
 }
@@ -296,7 +301,7 @@ int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const f
 
 // render_fwd.cu / render_bwd.cu
 int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char* geom,
-                              const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL, char* img,
+                              const GofGeomLayout& GL, char* bin, const GofBinLayout& BL, char* img,
                               const GofImageLayout& IL, float* out_color, cudaStream_t st);
 int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geom,
                                const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL,

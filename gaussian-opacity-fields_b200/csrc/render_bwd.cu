@@ -3,10 +3,11 @@
 // The reference issues 17 global float atomics per contributing (pixel,Gaussian) pair
 // (backward.cu:836,905-912,943-952).  Here a warp owns an 8x4 pixel block; the partial gradients of its 32
 // pixels are summed with a 16-shuffle butterfly (dL_dopacity is -2/opacity * dL_dC, so 16 values carry all
-// 17 outputs) and leave the SM as at most 17 atomics per (warp,Gaussian).  Pairs are re-evaluated with exactly
-// the forward's operation sequence (gof_math.cuh) so that the recomputed alpha equals the forward's; the
-// traversal starts at the last Gaussian any pixel of the tile actually blended, warps skip Gaussians behind
-// their own deepest contributor and Gaussians whose alpha-support box (gof_cull_bbox) misses their pixels.
+// 17 outputs) and leave the SM as 16 atomics per (warp,Gaussian) into that Gaussian's 64-byte accumulator row.
+// The forward leaves, per (warp, tile-list entry), the mask of pixels that blended it (GofBinLayout::vmask): the
+// backward visits exactly those (no box test, no reject arithmetic -- 44 % of the forward's visits blend nothing),
+// re-evaluating t, G and alpha with the forward's operation sequence (gof_math.cuh) so that they are bit-identical.
+// The traversal starts at the last Gaussian any pixel of the tile blended.
 #include <stdlib.h>
 
 #include "gof_common.cuh"
@@ -26,6 +27,8 @@ struct BwdArgs {
   const uint32_t* ncontrib;  // [2][tiles*256]
   const float* dL_dpix;      // [9][H][W]
   size_t plane;
+  const uint32_t* vmask;   // [8][R]: lanes of warp w that blended list entry r in the forward
+  size_t R;
   float* grad_acc;     // [P][16]: dL_dview2gaussian[10] | dL_dcolor[3] | dL_dmean2D[3] (64-byte rows, zeroed per call)
   unsigned long long* stats;   // optional [8] counters (GOF_STATS=1), else nullptr
 };
@@ -70,7 +73,7 @@ __device__ __forceinline__ float warp_reduce16(const float (&a)[16], int lane) {
 template <bool STATS, int MINB>
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const BwdArgs a) {
   unsigned long long st_visit = 0, st_eval = 0, st_pass = 0, st_contrib = 0, st_anyhit = 0;
-  // 28 KB: rows of 112 bytes per staged Gaussian = GofSplat (64 B) | GofSplatBwd (32 B) | (thr, id, -, -); one row base
+  // 28 KB: rows of 112 bytes per staged Gaussian = GofSplat (64 B) | GofSplatBwd (32 B) | (-, id, -, -); one row base
   // register serves every load of a visit (see gof_smem_base)
   __shared__ float4 s_rec[BATCH][7];
   __shared__ uint32_t s_max;
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
   const float ry = gof_ray(pix_y, a.H, a.focal_y);
 
   const uint2 range = a.ranges[tile];
+  const uint32_t* vm_row = a.vmask + (size_t)warp * a.R + range.x;
   const size_t slot = (size_t)tile * 256 + threadIdx.x;
   const size_t HW = (size_t)a.H * a.W;
   const size_t pid = (size_t)pix_y * a.W + pix_x;
@@ -143,31 +147,29 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
       s_rec[threadIdx.x][0] = r0; s_rec[threadIdx.x][1] = r1; s_rec[threadIdx.x][2] = r2; s_rec[threadIdx.x][3] = r3;
       const float4* srcb = reinterpret_cast<const float4*>(a.splat_bwd + g);
       s_rec[threadIdx.x][4] = __ldg(srcb); s_rec[threadIdx.x][5] = __ldg(srcb + 1);
-      const float op = r2.z;
-      s_rec[threadIdx.x][6] = make_float4((op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000),
-                                          __uint_as_float(g), 0.f, 0.f);
+      s_rec[threadIdx.x][6] = make_float4(0.f, __uint_as_float(g), 0.f, 0.f);
     }
     __syncthreads();
 
     const int nb = toDo < BATCH ? toDo : BATCH;
-    // Sub-batches of 32: ballot the Gaussians that can reach this warp's 8x4 pixels AND lie in front of its deepest
-    // contributor, then visit only those (loop NOT unrolled: one copy of the ~10 KB body, see render_fwd.cu)
+    // Sub-batches of 32 staged Gaussians; the loop is NOT unrolled (one copy of the body, see render_fwd.cu)
 #pragma unroll 1
     for (int k = 0; k < BATCH / 32; ++k) {
       if (k * 32 >= nb) break;
       const int idx = k * 32 + lane;
-      const float4 qb = s_rec[idx][3];
+      // the forward recorded, per (warp, list entry), which pixels blended it: visit exactly those
       const uint32_t cidx = (uint32_t)(used - 1 - (i * BATCH + idx));
-      uint32_t m = __ballot_sync(0xffffffffu, idx < nb && cidx < warp_last &&
-                                                  box_hits(__float_as_uint(qb.z), __float_as_uint(qb.w), wx0, wy0, wx0 + 7, wy0 + 3));
+      const uint32_t my_mask = (idx < nb && cidx < warp_last) ? __ldg(vm_row + cidx) : 0u;
+      uint32_t m = __ballot_sync(0xffffffffu, my_mask != 0u);
       while (m) {
         const int j = k * 32 + __ffs(m) - 1;
         m &= m - 1;
         // zero-based index of this Gaussian in the tile list == the reference's `contributor` after its
         // decrement (backward.cu:763)
         const uint32_t contributor = (uint32_t)(used - 1 - (i * BATCH + j));
-        bool contrib = inside && contributor < last_contributor;
-        if (STATS) { st_visit += (lane == 0); st_eval += contrib; }
+        const uint32_t lanes = __shfl_sync(0xffffffffu, my_mask, j & 31);
+        bool contrib = ((lanes >> lane) & 1u) != 0u;   // implies inside && contributor < last_contributor
+        if (STATS) { st_visit += (lane == 0); st_eval += contrib; st_pass += contrib; }
 
         const uint32_t row = s_base + (uint32_t)j * 112u;
         const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
@@ -176,26 +178,14 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         float t = 0.f, G = 0.f, alpha = 0.f;
         double qd = 0.0, rA = 0.0;
         if (contrib) {
+          // re-evaluated with the forward's operation sequence: bit-identical t, G, alpha
           p = gof_pair_geom(v, rx, ry);
-          const float bh = 0.5f * p.BB;
-          const float qf = bh * bh * gof_rcp_approx(p.AA);   // error bound: see render_fwd.cu
-          const float pw = -0.5f * (v[9] - qf);
-          const float bound = fmaf(fabsf(qf), 3.5e-7f, pw);
-          if (bound < gof_lds32<96>(row) && fabsf(p.AA) < 1e30f) contrib = false;
-        }
-        if (STATS) st_pass += contrib;
-        if (contrib) {
           float power;
           gof_pair_t_power(p, v[9], &t, &power, &qd, &rA);
-          if (GOF_T_BEHIND_NEAR(t)) contrib = false;
-          else {
-            G = F_EXP(power);
-            alpha = fminf(F_MUL(q2.z, G), GOF_ALPHA_MAX);
-            if (alpha < GOF_ALPHA_MIN) contrib = false;
-          }
+          G = F_EXP(power);
+          alpha = fminf(F_MUL(q2.z, G), GOF_ALPHA_MAX);
         }
         if (STATS) st_contrib += contrib;
-        if (!__any_sync(0xffffffffu, contrib)) continue;
         if (STATS) st_anyhit += (lane == 0);
 
         float g[16];
@@ -309,6 +299,8 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geo
   a.ncontrib = reinterpret_cast<const uint32_t*>(img + IL.ncontrib);
   a.dL_dpix = dL_dpix;
   a.plane = (size_t)v.tiles * 256;
+  a.vmask = reinterpret_cast<const uint32_t*>(bin + BL.vmask);
+  a.R = BL.vmask_R;
   a.grad_acc = reinterpret_cast<float*>(geom + GL.grad_acc);
   GOF_CUDA_OK(cudaMemsetAsync(a.grad_acc, 0, (size_t)s->P * 64, st));
   a.stats = gof_stats_buffer();

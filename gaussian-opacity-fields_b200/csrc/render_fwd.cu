@@ -32,6 +32,8 @@ struct FwdArgs {
   uint32_t* ncontrib;  // [2][tiles*256]
   float* out_color;    // [9][H][W]
   size_t plane;        // tiles*256
+  uint32_t* vmask;     // [8][R]: lanes of warp w that blended list entry r (read by the backward)
+  size_t R;
 };
 
 constexpr int BATCH = GOF_BLOCK_SIZE;
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
 
   const uint2 range = a.ranges[tile];
   const int total = (int)(range.y - range.x);
+  uint32_t* vm_row = a.vmask + (size_t)warp * a.R + range.x;   // this warp's masks for the tile's list entries
   const int rounds = (total + BATCH - 1) / BATCH;
 
   float T = 1.0f;
@@ -116,59 +119,66 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
       while (m) {
         const int j = k * 32 + __ffs(m) - 1;
         m &= m - 1;
-        if (done) continue;
-        const uint32_t contributor = (uint32_t)(i * BATCH + j + 1);   // 1-based position in the tile list
-        const uint32_t row = s_base + (uint32_t)j * 80u;
-        const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
-        const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-        const GofPair p = gof_pair_geom(v, rx, ry);
+        // No `continue` below: every lane reaches the ballot at the end of the visit, which records for the backward
+        // which pixels of this warp blended this Gaussian.
+        bool blended = false;
+        if (!done) {
+          const uint32_t contributor = (uint32_t)(i * BATCH + j + 1);   // 1-based position in the tile list
+          const uint32_t row = s_base + (uint32_t)j * 80u;
+          const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
+          const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+          const GofPair p = gof_pair_geom(v, rx, ry);
 
-        // ---- conservative reject (single precision, error-bounded) ----
-        {
+          // ---- conservative reject (single precision, error-bounded) ----
           const float bh = 0.5f * p.BB;
           // ~ BB^2/(4AA): bh*bh (1/2 ulp), MUFU.RCP (1 ulp, AA denormal -> inf -> not rejected), product (1/2 ulp):
           // relative error <= 2.4e-7 < 3.5e-7
           const float qf = bh * bh * gof_rcp_approx(p.AA);
           const float pw = -0.5f * (v[9] - qf);                  // approximate power
           const float bound = fmaf(fabsf(qf), 3.5e-7f, pw);      // pw + |error|
-          if (bound < gof_lds32<64>(row) && fabsf(p.AA) < 1e30f) continue;
+          if (!(bound < gof_lds32<64>(row) && fabsf(p.AA) < 1e30f)) {
+            // ---- exact path: forward.cu:516-541 ----
+            float t, power;
+            gof_pair_t_power(p, v[9], &t, &power);
+            if (!GOF_T_BEHIND_NEAR(t)) {
+              const float alpha = fminf(F_MUL(q2.z, F_EXP(power)), GOF_ALPHA_MAX);
+              if (!(alpha < GOF_ALPHA_MIN)) {
+                const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
+                if (test_T < GOF_T_EPS) {
+                  done = true;
+                } else {
+                  // forward.cu:543-578 (accumulation order = the reference's SASS: fma onto T)
+                  const float mt = gof_mapped_t_fast(t);
+                  const float rlen = gof_normal_rlen_fast(p);
+                  const float nn0 = p.n0 * rlen, nn1 = p.n1 * rlen, nn2 = p.n2 * rlen;
+                  const float A = F_SUB(1.0f, T);
+                  const float m2 = F_MUL(mt, mt);
+                  const float err = F_FMA(-dist1, F_ADD(mt, mt), F_FMA(A, m2, dist2));
+                  distortion = F_FMA(T, F_MUL(err, alpha), distortion);
+                  dist1 = F_FMA(T, F_MUL(alpha, mt), dist1);
+                  dist2 = F_FMA(T, F_MUL(m2, alpha), dist2);
+                  const float2 q3 = gof_lds64<48>(row);   // rgb1, rgb2
+                  C0 = F_FMA(T, F_MUL(alpha, q2.w), C0);
+                  C1 = F_FMA(T, F_MUL(alpha, q3.x), C1);
+                  C2 = F_FMA(T, F_MUL(alpha, q3.y), C2);
+                  N0 = F_FMA(-T, F_MUL(alpha, nn0), N0);
+                  N1 = F_FMA(-T, F_MUL(alpha, nn1), N1);
+                  N2 = F_FMA(-T, F_MUL(alpha, nn2), N2);
+                  if (T > 0.5f) {
+                    Dm = t;
+                    max_contributor = contributor;
+                  }
+                  Aacc = F_FMA(T, alpha, Aacc);
+                  T = test_T;
+                  last_contributor = contributor;
+                  blended = true;
+                }
+              }
+            }
+          }
         }
-
-        // ---- exact path: forward.cu:516-541 ----
-        float t, power;
-        gof_pair_t_power(p, v[9], &t, &power);
-        if (GOF_T_BEHIND_NEAR(t)) continue;
-        const float alpha = fminf(F_MUL(q2.z, F_EXP(power)), GOF_ALPHA_MAX);
-        if (alpha < GOF_ALPHA_MIN) continue;
-        const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
-        if (test_T < GOF_T_EPS) {
-          done = true;
-          continue;
-        }
-        // forward.cu:543-578 (accumulation order = the reference's SASS: fma onto T)
-        const float mt = gof_mapped_t_fast(t);
-        const float rlen = gof_normal_rlen_fast(p);
-        const float nn0 = p.n0 * rlen, nn1 = p.n1 * rlen, nn2 = p.n2 * rlen;
-        const float A = F_SUB(1.0f, T);
-        const float m2 = F_MUL(mt, mt);
-        const float err = F_FMA(-dist1, F_ADD(mt, mt), F_FMA(A, m2, dist2));
-        distortion = F_FMA(T, F_MUL(err, alpha), distortion);
-        dist1 = F_FMA(T, F_MUL(alpha, mt), dist1);
-        dist2 = F_FMA(T, F_MUL(m2, alpha), dist2);
-        const float2 q3 = gof_lds64<48>(row);   // rgb1, rgb2
-        C0 = F_FMA(T, F_MUL(alpha, q2.w), C0);
-        C1 = F_FMA(T, F_MUL(alpha, q3.x), C1);
-        C2 = F_FMA(T, F_MUL(alpha, q3.y), C2);
-        N0 = F_FMA(-T, F_MUL(alpha, nn0), N0);
-        N1 = F_FMA(-T, F_MUL(alpha, nn1), N1);
-        N2 = F_FMA(-T, F_MUL(alpha, nn2), N2);
-        if (T > 0.5f) {
-          Dm = t;
-          max_contributor = contributor;
-        }
-        Aacc = F_FMA(T, alpha, Aacc);
-        T = test_T;
-        last_contributor = contributor;
+        const uint32_t bm = __ballot_sync(0xffffffffu, blended);
+        if (bm != 0u && lane == 0) vm_row[i * BATCH + j] = bm;
       }
     }
   }
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
 }  // namespace
 
 int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char* geom, const GofGeomLayout& GL,
-                              const char* bin, const GofBinLayout& BL, char* img, const GofImageLayout& IL,
+                              char* bin, const GofBinLayout& BL, char* img, const GofImageLayout& IL,
                               float* out_color, cudaStream_t st) {
   FwdArgs a;
   a.W = v.W; a.H = v.H; a.grid_x = v.grid_x; a.focal_x = v.focal_x; a.focal_y = v.focal_y;
@@ -213,6 +223,9 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
   a.ncontrib = reinterpret_cast<uint32_t*>(img + IL.ncontrib);
   a.out_color = out_color;
   a.plane = (size_t)v.tiles * 256;
+  a.vmask = reinterpret_cast<uint32_t*>(bin + BL.vmask);
+  a.R = BL.vmask_R;
+  if (a.R) GOF_CUDA_OK(cudaMemsetAsync(a.vmask, 0, a.R * 32, st));
   static int occ = -1;   // GOF_FWD_OCC=3|4: resident CTAs per SM the kernel is compiled for (tuning knob)
   if (occ < 0) { const char* e = getenv("GOF_FWD_OCC"); occ = e ? atoi(e) : 4; }
   if (occ >= 4) GOF_LAUNCH("render_fwd", st, k_render_forward<4><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
