@@ -197,9 +197,11 @@ struct GofBinLayout {       // "binningBuffer": everything sized by R = num_rend
   int bits[4];              // digit widths, low digit first
   size_t point_list;        // offset of the final sorted Gaussian-id list (val_a or val_b)
   size_t sorted_keys;       // offset of the final sorted tile-id list
-  size_t vmask_R;           // = R
-  size_t vmask;             // u32[8][R]: for warp w of the tile and list entry r, the lanes (pixels) that blended it in
-                            // the forward; written by k_render_forward, the backward visits exactly those
+  size_t vmask_stride;      // = R + 32 * tiles (u32 elements per warp plane)
+  size_t vmask;             // u32[8][R + 32*tiles]: blend masks left by k_render_forward for the backward.  A tile's list is
+                            // cut into groups of 32 entries; for warp w, group g of tile t, lane l the word at
+                            // w*stride + ranges[t].x + 32*t + 32*g + l holds, bit b, "pixel l blended entry 32*g+b".
+                            // (32 words of slack per tile: its last group may be partial)
   size_t bytes;
 };
 
@@ -231,8 +233,8 @@ static inline GofBinLayout gof_bin_layout(size_t R, int W, int H) {
   L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(R) + 1) * 4);
   L.point_list = (L.passes % 2 == 0) ? L.val_a : L.val_b;
   L.sorted_keys = (L.passes % 2 == 0) ? L.key_a : L.key_b;
-  L.vmask_R = R;
-  L.vmask = take(R * 32);
+  L.vmask_stride = R + 32 * (size_t)tiles;
+  L.vmask = take(L.vmask_stride * 32);
   L.bytes = o;
   return L;
 }

@@ -27,8 +27,8 @@ struct BwdArgs {
   const uint32_t* ncontrib;  // [2][tiles*256]
   const float* dL_dpix;      // [9][H][W]
   size_t plane;
-  const uint32_t* vmask;   // [8][R]: lanes of warp w that blended list entry r in the forward
-  size_t R;
+  const uint32_t* vmask;   // blend masks left by the forward (GofBinLayout::vmask)
+  size_t vstride;
   float* grad_acc;     // [P][16]: dL_dview2gaussian[10] | dL_dcolor[3] | dL_dmean2D[3] (64-byte rows, zeroed per call)
   unsigned long long* stats;   // optional [8] counters (GOF_STATS=1), else nullptr
 };
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
   const float ry = gof_ray(pix_y, a.H, a.focal_y);
 
   const uint2 range = a.ranges[tile];
-  const uint32_t* vm_row = a.vmask + (size_t)warp * a.R + range.x;
+  const uint32_t* vm_row = a.vmask + (size_t)warp * a.vstride + range.x + 32u * (uint32_t)tile + lane;   // + 32*group
   const size_t slot = (size_t)tile * 256 + threadIdx.x;
   const size_t HW = (size_t)a.H * a.W;
   const size_t pid = (size_t)pix_y * a.W + pix_x;
@@ -135,13 +135,14 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
   //   v 10..12 -> dL_dcolor, v 13..15 -> dL_dmean2D
   const int vidx = lane >> 1;
 
-  int toDo = used;
-  for (int i = 0; i < rounds; ++i, toDo -= BATCH) {
+  // Batches are the forward's (entries [256*ib, 256*ib+256) of the tile list), taken from the deepest one the tile used
+  // down to 0; inside a batch the groups of 32 and the bits inside a group are walked from high to low: back to front.
+  for (int i = 0; i < rounds; ++i) {
+    const int ib = rounds - 1 - i;
+    const int base = ib * BATCH;
     __syncthreads();
-    // stage batch i in REVERSE order: element j of the batch is list entry used-1-(i*BATCH+j)
-    const int progress = i * BATCH + (int)threadIdx.x;
-    if (progress < used) {
-      const uint32_t g = a.point_list[range.x + (uint32_t)(used - 1 - progress)];
+    if (base + (int)threadIdx.x < used) {
+      const uint32_t g = a.point_list[range.x + (uint32_t)(base + (int)threadIdx.x)];
       const float4* src = reinterpret_cast<const float4*>(a.splat + g);
       const float4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
       s_rec[threadIdx.x][0] = r0; s_rec[threadIdx.x][1] = r1; s_rec[threadIdx.x][2] = r2; s_rec[threadIdx.x][3] = r3;
@@ -151,24 +152,22 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
     }
     __syncthreads();
 
-    const int nb = toDo < BATCH ? toDo : BATCH;
-    // Sub-batches of 32 staged Gaussians; the loop is NOT unrolled (one copy of the body, see render_fwd.cu)
+    // the loop is NOT unrolled (one copy of the body, see render_fwd.cu)
 #pragma unroll 1
-    for (int k = 0; k < BATCH / 32; ++k) {
-      if (k * 32 >= nb) break;
-      const int idx = k * 32 + lane;
-      // the forward recorded, per (warp, list entry), which pixels blended it: visit exactly those
-      const uint32_t cidx = (uint32_t)(used - 1 - (i * BATCH + idx));
-      const uint32_t my_mask = (idx < nb && cidx < warp_last) ? __ldg(vm_row + cidx) : 0u;
-      uint32_t m = __ballot_sync(0xffffffffu, my_mask != 0u);
+    for (int k = BATCH / 32 - 1; k >= 0; --k) {
+      const int gstart = base + k * 32;
+      // the forward wrote the masks of every group up to this warp's deepest contributor; nothing behind it blended
+      if ((uint32_t)gstart >= warp_last) continue;
+      const uint32_t mybits = __ldg(vm_row + gstart);        // bit b: this pixel blended entry gstart+b
+      uint32_t m = __reduce_or_sync(0xffffffffu, mybits);
       while (m) {
-        const int j = k * 32 + __ffs(m) - 1;
-        m &= m - 1;
+        const int b = 31 - __clz(m);
+        m &= ~(1u << b);
+        const int j = k * 32 + b;
         // zero-based index of this Gaussian in the tile list == the reference's `contributor` after its
         // decrement (backward.cu:763)
-        const uint32_t contributor = (uint32_t)(used - 1 - (i * BATCH + j));
-        const uint32_t lanes = __shfl_sync(0xffffffffu, my_mask, j & 31);
-        bool contrib = ((lanes >> lane) & 1u) != 0u;   // implies inside && contributor < last_contributor
+        const uint32_t contributor = (uint32_t)(gstart + b);
+        bool contrib = ((mybits >> b) & 1u) != 0u;   // implies inside && contributor < last_contributor
         if (STATS) { st_visit += (lane == 0); st_eval += contrib; st_pass += contrib; }
 
         const uint32_t row = s_base + (uint32_t)j * 112u;
@@ -300,7 +299,7 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geo
   a.dL_dpix = dL_dpix;
   a.plane = (size_t)v.tiles * 256;
   a.vmask = reinterpret_cast<const uint32_t*>(bin + BL.vmask);
-  a.R = BL.vmask_R;
+  a.vstride = BL.vmask_stride;
   a.grad_acc = reinterpret_cast<float*>(geom + GL.grad_acc);
   GOF_CUDA_OK(cudaMemsetAsync(a.grad_acc, 0, (size_t)s->P * 64, st));
   a.stats = gof_stats_buffer();

@@ -32,8 +32,8 @@ struct FwdArgs {
   uint32_t* ncontrib;  // [2][tiles*256]
   float* out_color;    // [9][H][W]
   size_t plane;        // tiles*256
-  uint32_t* vmask;     // [8][R]: lanes of warp w that blended list entry r (read by the backward)
-  size_t R;
+  uint32_t* vmask;     // blend masks for the backward (GofBinLayout::vmask)
+  size_t vstride;
 };
 
 constexpr int BATCH = GOF_BLOCK_SIZE;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
 
   const uint2 range = a.ranges[tile];
   const int total = (int)(range.y - range.x);
-  uint32_t* vm_row = a.vmask + (size_t)warp * a.R + range.x;   // this warp's masks for the tile's list entries
+  uint32_t* vm_row = a.vmask + (size_t)warp * a.vstride + range.x + 32u * (uint32_t)tile + lane;   // + 32*group
   const int rounds = (total + BATCH - 1) / BATCH;
 
   float T = 1.0f;
@@ -116,11 +116,11 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
       const int idx = k * 32 + lane;
       const float4 qb = s_rec[idx][3];
       uint32_t m = __ballot_sync(0xffffffffu, idx < nb && box_hits(__float_as_uint(qb.z), __float_as_uint(qb.w), wx0, wy0, wx0 + 7, wy0 + 3));
+      uint32_t mybits = 0u;   // bit b: this pixel blended entry k*32+b of the batch
       while (m) {
-        const int j = k * 32 + __ffs(m) - 1;
+        const int b = __ffs(m) - 1;
+        const int j = k * 32 + b;
         m &= m - 1;
-        // No `continue` below: every lane reaches the ballot at the end of the visit, which records for the backward
-        // which pixels of this warp blended this Gaussian.
         bool blended = false;
         if (!done) {
           const uint32_t contributor = (uint32_t)(i * BATCH + j + 1);   // 1-based position in the tile list
@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
             }
           }
         }
-        const uint32_t bm = __ballot_sync(0xffffffffu, blended);
-        if (bm != 0u && lane == 0) vm_row[i * BATCH + j] = bm;
+        if (blended) mybits |= 1u << b;
       }
+      vm_row[i * BATCH + k * 32] = mybits;   // one coalesced 128-byte store per (warp, group): the backward's work list
     }
   }
 
@@ -224,8 +224,7 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
   a.out_color = out_color;
   a.plane = (size_t)v.tiles * 256;
   a.vmask = reinterpret_cast<uint32_t*>(bin + BL.vmask);
-  a.R = BL.vmask_R;
-  if (a.R) GOF_CUDA_OK(cudaMemsetAsync(a.vmask, 0, a.R * 32, st));
+  a.vstride = BL.vmask_stride;
   static int occ = -1;   // GOF_FWD_OCC=3|4: resident CTAs per SM the kernel is compiled for (tuning knob)
   if (occ < 0) { const char* e = getenv("GOF_FWD_OCC"); occ = e ? atoi(e) : 4; }
   if (occ >= 4) GOF_LAUNCH("render_fwd", st, k_render_forward<4><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
