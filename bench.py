@@ -143,6 +143,21 @@ def bwd_args(fa, radii, geom, R, binning, img, grad):
             campos, geom, R, binning, img, dbg)
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` at this workload, from the committed
+    `ncu --set full` summary (profiles/r1_final_<kernel>.txt); None if the file is missing."""
+    path = os.path.join(ROOT, "profiles", f"r1_final_{kernel}.txt")
+    try:
+        tot = 0.0
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(P, V, R, N):
     """bytes one fwd+bwd view must move, and the share of the backward blend kernel."""
     step = 52 * P + 962 * V + 188 * R + 120 * N
@@ -271,6 +286,20 @@ def run_ours(args, rank, world, dev):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     assert all(math.isfinite(x) for x in losses), "non-finite loss in the end-to-end loop"
 
+    # the exchange step alone (N > 1): one all-reduce of the 59-float/Gaussian gradient bucket, CUDA events, max over ranks
+    allreduce_ms = None
+    if world > 1:
+        for _ in range(3):
+            bucket.all_reduce()
+        barrier_sync(world)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            bucket.all_reduce()
+        a1.record()
+        barrier_sync(world)
+        allreduce_ms = max_over_ranks(a0.elapsed_time(a1) / 10, world, dev)
+
     step_bytes, fwd_bytes, bwd_bytes = algorithmic_bytes(wl.P, V, R, N)
     peaks = {}
     try:
@@ -297,13 +326,16 @@ def run_ours(args, rank, world, dev):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(dom),
+                     "traffic_source": f"profiles/r1_final_{dom}.txt (ncu --set full, same workload, per launch)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms / max(dom_cnt, 1),
                      "step_algorithmic_bytes": step_bytes,
                      "step_frac": step_bytes / ((ms / args.steps) * 1e-3) / 1e9 / peak},
         "kernels_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
+    if allreduce_ms is not None:
+        line["exchange"] = {"what": "all-reduce(SUM) of 59 f32 per Gaussian (NCCL)", "bytes": int(wl.P) * 59 * 4, "ms": allreduce_ms}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, full=False)
     return line
