@@ -173,6 +173,18 @@ def run_ours(args, rank, world, dev):
 
     wl = Workload(args.config, dev, rank, world)
     bucket = gof_dp.GradBucket(wl.P, 16, dev)
+    exchange_note = None
+    if world > 1 and args.exchange == "p2p":
+        try:
+            bucket.enable_peer_exchange()
+        except Exception as e:   # e.g. no peer access between the GPUs of this box: say so and use NCCL
+            exchange_note = f"peer mapping failed ({type(e).__name__}: {e}); NCCL all-reduce used"
+            ok = torch.tensor([0.0], device=dev)
+        else:
+            ok = torch.tensor([1.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            bucket.exchange = "nccl"
     stats = {}
 
     def step_device(step):
@@ -335,7 +347,11 @@ def run_ours(args, rank, world, dev):
         "kernels_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
     if allreduce_ms is not None:
-        line["exchange"] = {"what": "all-reduce(SUM) of 59 f32 per Gaussian (NCCL)", "bytes": int(wl.P) * 59 * 4, "ms": allreduce_ms}
+        what = ("sum of 59 f32 per Gaussian by the library's kernel over NVLink peer memory (csrc/exchange.cu), two NCCL barriers"
+                if bucket.exchange == "p2p" else "all-reduce(SUM) of 59 f32 per Gaussian (NCCL)")
+        line["exchange"] = {"impl": bucket.exchange, "what": what, "bytes": int(wl.P) * 59 * 4, "ms": allreduce_ms}
+        if exchange_note:
+            line["exchange"]["note"] = exchange_note
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, full=False)
     return line
@@ -466,6 +482,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(gof_synth.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: gradient exchange by the library's NVLink peer-memory kernel (default) or NCCL's all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():

@@ -1,0 +1,76 @@
+// exchange.cu -- the one exchange step of view-parallel training: the sum over ranks of the flat
+// per-Gaussian gradient bucket (59 floats per Gaussian), done by ONE kernel over NVLink peer memory instead of a
+// library all-reduce.  No reference counterpart (the reference is single-GPU).
+//
+// Every rank's bucket is mapped into every process (CUDA IPC).  Rank r owns the r-th 1/N slice of the index space:
+// it loads that slice from all N buckets (N-1 of them over NVLink), adds them in rank order 0..N-1 -- so every rank
+// ends with bit-identical sums -- and stores the result into all N buckets.  Slices are disjoint, so inside the
+// kernel no location is touched by two ranks; the caller brackets the launch with two cross-rank barriers
+// (all buckets complete before / all slices written after).  Per GPU: (N-1)/N of the bucket in and the same out.
+#include <stdint.h>
+
+#include "gof_common.cuh"
+
+namespace {
+
+constexpr int GOF_MAX_PEERS = 8;
+struct PeerPtrs { float4* p[GOF_MAX_PEERS]; };
+
+__device__ __forceinline__ float4 ld_cg(const float4* p) { return __ldcg(p); }   // L2 only: peer data is never L1-cached
+
+template <int W>
+__global__ void __launch_bounds__(512) k_p2p_allreduce(const PeerPtrs a, size_t begin, size_t end) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    float4 v[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r) v[r] = ld_cg(a.p[r] + i);
+    float4 s = v[0];
+#pragma unroll
+    for (int r = 1; r < W; ++r) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+#pragma unroll
+    for (int r = 0; r < W; ++r) __stcg(a.p[r] + i, s);
+  }
+}
+
+// generic world size (3, 5, 6, 7): same scheme, runtime loop
+__global__ void __launch_bounds__(512) k_p2p_allreduce_any(const PeerPtrs a, int world, size_t begin, size_t end) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    float4 s = ld_cg(a.p[0] + i);
+    for (int r = 1; r < world; ++r) { const float4 v = ld_cg(a.p[r] + i); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    for (int r = 0; r < world; ++r) __stcg(a.p[r] + i, s);
+  }
+}
+
+}  // namespace
+
+// peers[r] = address (in THIS process) of rank r's bucket, r = 0..world-1; n = floats per bucket (multiple of 4,
+// 16-byte aligned buffers).  Reduces this rank's slice; the caller provides the two cross-rank barriers.
+extern "C" GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, size_t n, void* stream) {
+  if (!peers || world < 1 || world > GOF_MAX_PEERS || rank < 0 || rank >= world || (n & 3u)) {
+    gof_set_error("p2p_allreduce: bad arguments (world 1..8, n multiple of 4)");
+    return GOF_E_INVALID;
+  }
+  if (world == 1 || n == 0) return GOF_OK;
+  PeerPtrs a;
+  for (int r = 0; r < GOF_MAX_PEERS; ++r) a.p[r] = reinterpret_cast<float4*>(r < world ? peers[r] : nullptr);
+  for (int r = 0; r < world; ++r)
+    if (!a.p[r] || (reinterpret_cast<uintptr_t>(a.p[r]) & 15u)) { gof_set_error("p2p_allreduce: peer pointer NULL or unaligned"); return GOF_E_INVALID; }
+  const size_t n4 = n / 4;
+  const size_t begin = n4 * (size_t)rank / (size_t)world, end = n4 * (size_t)(rank + 1) / (size_t)world;
+  if (end <= begin) return GOF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const size_t want = (end - begin + 511) / 512;
+  const unsigned grid = (unsigned)(want < (size_t)sms * 4 ? want : (size_t)sms * 4);
+  switch (world) {
+    case 2: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<2><<<grid, 512, 0, st>>>(a, begin, end)); break;
+    case 4: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<4><<<grid, 512, 0, st>>>(a, begin, end)); break;
+    case 8: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<8><<<grid, 512, 0, st>>>(a, begin, end)); break;
+    default: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce_any<<<grid, 512, 0, st>>>(a, world, begin, end)); break;
+  }
+  GOF_LAUNCH_CHECK(false, st);
+  return GOF_OK;
+}

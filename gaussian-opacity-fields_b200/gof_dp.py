@@ -5,7 +5,13 @@ The reference is single-GPU (its only multi-GPU use is one training job per GPU,
 so this module is new, not a port.  It uses torch.distributed (NCCL on GPUs, gloo in the CPU tests); the
 rasterizer backward writes its outputs directly into views of the flat buffer (`_out=` of
 `_C.rasterize_gaussians_backward`), so there is no pack/copy step before the collective.
+
+Exchange step: `GradBucket.all_reduce()` is NCCL's all-reduce.  `GradBucket.enable_peer_exchange()` switches it to the
+library's own kernel over NVLink peer memory (csrc/exchange.cu: every rank maps every rank's bucket through CUDA IPC,
+reduces its 1/N slice from all of them in rank order and stores it into all of them), bracketed by two NCCL barriers.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -22,7 +28,7 @@ class GradBucket:
         for name, tail in _FIELDS:
             shapes[name] = (self.P, self.M, 3) if name == "dsh" else (self.P,) + tail
         self.numel = sum(int(torch.Size(s).numel()) for s in shapes.values())
-        self.flat = torch.zeros(self.numel, dtype=dtype, device=device)
+        self.flat = torch.zeros((self.numel + 3) // 4 * 4, dtype=dtype, device=device)   # float4 granularity for the peer kernel
         self.views = {}
         off = 0
         for name, shape in shapes.items():
@@ -30,12 +36,61 @@ class GradBucket:
             self.views[name] = self.flat[off:off + n].view(shape)
             off += n
 
+        self._peers = None       # tensors mapping every rank's flat buffer (CUDA IPC), index = rank
+        self._peer_ptrs = None
+        self._sync = None
+        self.exchange = "nccl"
+
     def zero_(self):
         self.flat.zero_()
+
+    def enable_peer_exchange(self, group=None):
+        """Map every rank's bucket into this process (one node, CUDA IPC over NVLink) so that all_reduce() can run the
+        library's peer-memory kernel.  Collective: every rank of `group` must call it.  Raises if the mapping fails."""
+        from torch.multiprocessing.reductions import reduce_tensor
+        from diff_gaussian_rasterization import _C
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self
+        if not self.flat.is_cuda or self.flat.dtype != torch.float32:
+            raise RuntimeError("peer exchange needs a CUDA float32 bucket")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > 8:
+            raise RuntimeError("peer exchange: at most 8 ranks (one NVSwitch domain)")
+        # the bucket must start a 16-byte aligned, float4-sized region
+        if self.flat.data_ptr() % 16 or self.flat.numel() % 4:
+            raise RuntimeError("peer exchange: bucket must be 16-byte aligned with a multiple of 4 elements")
+        handles = [None] * world
+        dist.all_gather_object(handles, reduce_tensor(self.flat), group=group)
+        peers = []
+        for r, (fn, args) in enumerate(handles):
+            peers.append(self.flat if r == rank else fn(*args))
+        for r, t in enumerate(peers):
+            if t.numel() != self.flat.numel() or t.dtype != torch.float32:
+                raise RuntimeError(f"peer exchange: rank {r} shares a bucket of a different size")
+        self._peers = peers
+        self._peer_ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in peers])
+        self._sync = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
+        lib = _C._lib
+        lib.gof_p2p_allreduce_sum_f32.restype = ctypes.c_int
+        lib.gof_p2p_allreduce_sum_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        self._lib, self._check, self._world, self._rank = lib, _C._check, world, rank
+        self.exchange = "p2p"
+        dist.barrier(group=group)
+        return self
 
     def all_reduce(self, group=None, async_op=False):
         """Sum over ranks.  World size 1: no-op."""
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return None
+        if self.exchange == "p2p":
+            # barrier: every rank's backward has filled its bucket (a 4-byte NCCL all-reduce on the same stream orders it
+            # after the local kernels and completes only when every rank has reached it)
+            dist.all_reduce(self._sync, group=group)
+            with torch.cuda.device(self.flat.device):
+                self._check(self._lib.gof_p2p_allreduce_sum_f32(self._peer_ptrs, self._world, self._rank, self.flat.numel(),
+                                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            # barrier: every slice has been written into every bucket
+            dist.all_reduce(self._sync, group=group)
             return None
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 

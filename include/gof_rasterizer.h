@@ -169,6 +169,13 @@ GOF_API int gof_profile_timeline(char* buf, int cap);
 /* GOF_STATS=1 only: copies the 8 pair counters of the backward blend to `out` (host) and clears them; 0 if disabled. */
 GOF_API int gof_stats_read(unsigned long long* out);
 
+/* The exchange step of view-parallel training (no reference counterpart: the reference is single-GPU): sum over
+ * ranks of a flat f32 buffer over NVLink peer memory.  peers[r] = address, valid in THIS process, of rank r's buffer
+ * (CUDA IPC mapping; peers[rank] is the local one); n = floats per buffer (multiple of 4, 16-byte aligned).  This
+ * rank reduces its 1/world slice from all buffers (rank order 0..world-1: bit-identical results everywhere) and
+ * stores it into all of them.  The caller brackets the call with two cross-rank barriers on `stream`. */
+GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, size_t n, void* stream);
+
 GOF_API const char* gof_last_error(void);
 GOF_API int gof_version(void);
 

@@ -53,3 +53,33 @@ def test_full_size_against_live_reference(ref, name, view):
         noise = _util.rel_err(c, b)[0]
         err = _util.rel_err(a, b)[0]
         assert err <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {err}, ref-vs-ref {noise}"
+
+
+@pytest.mark.parametrize("M,deg", [(4, 1), (9, 2), (16, 2)])
+def test_sh_layouts_against_live_reference(ref, M, deg):
+    """SH tensors with M != 16 coefficients / degree below the maximum (scalar load path and partial dL_dsh rows of
+    k_preprocess_backward), P not a multiple of the warp size, and backward called twice on the same saved buffers."""
+    from diff_gaussian_rasterization import _C as ours
+    dev = torch.device("cuda")
+    cam, gs = gof_synth.make_scene(dict(P=30_011, width=400, height=300, seed=21), view=11)
+    gs = dict(gs)
+    gs["shs"] = gs["shs"][:, :M, :].contiguous()
+    fa = _util.fwd_args(cam, gs, dev, sh_degree=deg)
+    Ro, co, rado, geo, bino, imo = ours.rasterize_gaussians(*fa)
+    Rr, cr, radr, ger, binr, imr = ref.rasterize_gaussians(*fa)
+    assert Ro == Rr and torch.equal(rado, radr)
+    for ch in range(9):
+        assert _util.rel_err(co[ch], cr[ch])[0] < (2e-5 if ch == 8 else 2e-6), f"channel {ch}"
+    grad = torch.randn(9, 300, 400, generator=torch.Generator().manual_seed(3)).to(dev)
+    go = ours.rasterize_gaussians_backward(*_util.bwd_args(fa, rado, geo, Ro, bino, imo, grad))
+    go2 = ours.rasterize_gaussians_backward(*_util.bwd_args(fa, rado, geo, Ro, bino, imo, grad))
+    g1 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    g2 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    for n, a, a2, b, c in zip(NAMES, go, go2, g1, g2):
+        assert a.shape == b.shape, n
+        noise = _util.rel_err(c, b)[0]
+        assert _util.rel_err(a, b)[0] <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {_util.rel_err(a, b)[0]}, ref-vs-ref {noise}"
+        assert _util.rel_err(a2, a)[0] <= max(1e-5, 2.0 * noise), f"{n}: second backward on the same buffers differs"
+    # coefficients above the active degree receive no gradient (backward.cu:20-139 writes degree <= D only)
+    used = (deg + 1) ** 2
+    assert float(go[5][:, used:, :].abs().max()) == 0.0 if used < M else True
