@@ -482,8 +482,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(gof_synth.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: gradient exchange by the library's NVLink peer-memory kernel (default) or NCCL's all-reduce")
+    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
+                    help="N>1: gradient exchange by NCCL's all-reduce (default) or the library's NVLink peer-memory kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():

@@ -45,6 +45,22 @@ __global__ void __launch_bounds__(512) k_p2p_allreduce_any(const PeerPtrs a, int
 
 }  // namespace
 
+// Peer access from the current device to `peer_device` (the device index, in THIS process, on which a peer bucket was
+// mapped).  CUDA IPC mappings opened under the exporting device's context are not reachable from kernels of another
+// device until this has been called once.  Idempotent.
+extern "C" GOF_API int gof_enable_peer_access(int peer_device) {
+  int cur = 0;
+  GOF_CUDA_OK(cudaGetDevice(&cur));
+  if (peer_device == cur) return GOF_OK;
+  int can = 0;
+  GOF_CUDA_OK(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  if (!can) { gof_set_error("device %d cannot access device %d (no NVLink/PCIe peer path)", cur, peer_device); return GOF_E_INVALID; }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return GOF_OK; }
+  if (e != cudaSuccess) { gof_set_error("cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e)); return GOF_E_CUDA; }
+  return GOF_OK;
+}
+
 // peers[r] = address (in THIS process) of rank r's bucket, r = 0..world-1; n = floats per bucket (multiple of 4,
 // 16-byte aligned buffers).  Reduces this rank's slice; the caller provides the two cross-rank barriers.
 extern "C" GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, size_t n, void* stream) {

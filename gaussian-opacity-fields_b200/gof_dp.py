@@ -67,15 +67,29 @@ class GradBucket:
         for r, t in enumerate(peers):
             if t.numel() != self.flat.numel() or t.dtype != torch.float32:
                 raise RuntimeError(f"peer exchange: rank {r} shares a bucket of a different size")
+        lib = _C._lib
+        lib.gof_enable_peer_access.restype = ctypes.c_int
+        lib.gof_enable_peer_access.argtypes = [ctypes.c_int]
+        with torch.cuda.device(self.flat.device):
+            for t in peers:   # IPC mappings live under the exporting device's context: make them reachable from ours
+                _C._check(lib.gof_enable_peer_access(int(t.device.index)))
         self._peers = peers
         self._peer_ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in peers])
         self._sync = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
-        lib = _C._lib
         lib.gof_p2p_allreduce_sum_f32.restype = ctypes.c_int
         lib.gof_p2p_allreduce_sum_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
         self._lib, self._check, self._world, self._rank = lib, _C._check, world, rank
         self.exchange = "p2p"
         dist.barrier(group=group)
+        # self-test on the live mapping (the bucket content is scratch at this point): ones must sum to `world` everywhere
+        self.flat.fill_(1.0)
+        self.all_reduce(group=group)
+        torch.cuda.synchronize(self.flat.device)
+        good = bool((self.flat == float(world)).all().item())
+        self.flat.zero_()
+        if not good:
+            self.exchange = "nccl"
+            raise RuntimeError("peer exchange self-test failed")
         return self
 
     def all_reduce(self, group=None, async_op=False):

@@ -175,6 +175,9 @@ GOF_API int gof_stats_read(unsigned long long* out);
  * rank reduces its 1/world slice from all buffers (rank order 0..world-1: bit-identical results everywhere) and
  * stores it into all of them.  The caller brackets the call with two cross-rank barriers on `stream`. */
 GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, size_t n, void* stream);
+/* Enables peer access from the current device to `peer_device` (needed once per peer before kernels of this device
+ * may dereference that peer's IPC-mapped memory).  Idempotent. */
+GOF_API int gof_enable_peer_access(int peer_device);
 
 GOF_API const char* gof_last_error(void);
 GOF_API int gof_version(void);
