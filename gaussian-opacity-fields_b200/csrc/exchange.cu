@@ -61,6 +61,34 @@ extern "C" GOF_API int gof_enable_peer_access(int peer_device) {
   return GOF_OK;
 }
 
+// A bucket that other processes can map: plain cudaMalloc (its own allocation, so the IPC handle addresses it at offset
+// 0), zero-filled.  handle64 receives the 64-byte cudaIpcMemHandle_t to send to the peers.
+extern "C" GOF_API int gof_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || bytes == 0) { gof_set_error("peer_alloc: bad arguments"); return GOF_E_INVALID; }
+  void* p = nullptr;
+  GOF_CUDA_OK(cudaMalloc(&p, bytes));
+  GOF_CUDA_OK(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  GOF_CUDA_OK(cudaIpcGetMemHandle(&h, p));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return GOF_OK;
+}
+// Maps a peer's bucket into this process FOR THE CURRENT DEVICE (peer access to the exporting device is enabled by
+// the driver as part of the mapping -- the way NCCL's P2P transport opens its buffers).
+extern "C" GOF_API int gof_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) { gof_set_error("peer_open: bad arguments"); return GOF_E_INVALID; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  GOF_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr = p;
+  return GOF_OK;
+}
+extern "C" GOF_API int gof_peer_close(void* ptr) { if (ptr) GOF_CUDA_OK(cudaIpcCloseMemHandle(ptr)); return GOF_OK; }
+extern "C" GOF_API int gof_peer_free(void* ptr) { if (ptr) GOF_CUDA_OK(cudaFree(ptr)); return GOF_OK; }
+
 // peers[r] = address (in THIS process) of rank r's bucket, r = 0..world-1; n = floats per bucket (multiple of 4,
 // 16-byte aligned buffers).  Reduces this rank's slice; the caller provides the two cross-rank barriers.
 extern "C" GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, size_t n, void* stream) {

@@ -45,9 +45,9 @@ class GradBucket:
         self.flat.zero_()
 
     def enable_peer_exchange(self, group=None):
-        """Map every rank's bucket into this process (one node, CUDA IPC over NVLink) so that all_reduce() can run the
-        library's peer-memory kernel.  Collective: every rank of `group` must call it.  Raises if the mapping fails."""
-        from torch.multiprocessing.reductions import reduce_tensor
+        """Move the bucket into a CUDA-IPC shareable allocation, map every other rank's bucket into this process (one node,
+        NVLink) and switch all_reduce() to the library's peer-memory kernel.  Collective: every rank of `group` must call
+        it, before the views are handed to anyone (they are re-created).  Raises if mapping or the self-test fails."""
         from diff_gaussian_rasterization import _C
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return self
@@ -56,35 +56,47 @@ class GradBucket:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > 8:
             raise RuntimeError("peer exchange: at most 8 ranks (one NVSwitch domain)")
-        # the bucket must start a 16-byte aligned, float4-sized region
-        if self.flat.data_ptr() % 16 or self.flat.numel() % 4:
-            raise RuntimeError("peer exchange: bucket must be 16-byte aligned with a multiple of 4 elements")
-        handles = [None] * world
-        dist.all_gather_object(handles, reduce_tensor(self.flat), group=group)
-        peers = []
-        for r, (fn, args) in enumerate(handles):
-            peers.append(self.flat if r == rank else fn(*args))
-        for r, t in enumerate(peers):
-            if t.numel() != self.flat.numel() or t.dtype != torch.float32:
-                raise RuntimeError(f"peer exchange: rank {r} shares a bucket of a different size")
-        lib = _C._lib
-        lib.gof_enable_peer_access.restype = ctypes.c_int
-        lib.gof_enable_peer_access.argtypes = [ctypes.c_int]
-        with torch.cuda.device(self.flat.device):
-            for t in peers:   # IPC mappings live under the exporting device's context: make them reachable from ours
-                _C._check(lib.gof_enable_peer_access(int(t.device.index)))
-        self._peers = peers
-        self._peer_ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in peers])
-        self._sync = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
-        lib.gof_p2p_allreduce_sum_f32.restype = ctypes.c_int
+        lib, dev, n = _C._lib, self.flat.device, self.flat.numel()
+        for f in ("gof_peer_alloc", "gof_peer_open", "gof_p2p_allreduce_sum_f32"):
+            getattr(lib, f).restype = ctypes.c_int
+        lib.gof_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]
+        lib.gof_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
         lib.gof_p2p_allreduce_sum_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        ptr, handle = ctypes.c_void_p(0), ctypes.create_string_buffer(64)
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize()
+            _C._check(lib.gof_peer_alloc(n * 4, ctypes.byref(ptr), handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(ptr.value)
+                else:
+                    q = ctypes.c_void_p(0)
+                    _C._check(lib.gof_peer_open(handles[r], ctypes.byref(q)))
+                    ptrs.append(q.value)
+
+        class _Raw:   # zero-copy torch view of the cudaMalloc'ed bucket
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+        self._raw = _Raw()
+        old_views = self.views
+        self.flat = torch.as_tensor(self._raw, device=dev)
+        if self.flat.data_ptr() != ptr.value or self.flat.numel() != n:
+            raise RuntimeError("peer exchange: could not wrap the shared allocation")
+        self.views, off = {}, 0
+        for name, v in old_views.items():
+            self.views[name] = self.flat[off:off + v.numel()].view(v.shape)
+            off += v.numel()
+        self._peer_ptrs = (ctypes.c_void_p * world)(*ptrs)
+        self._sync = torch.zeros(1, dtype=torch.float32, device=dev)
         self._lib, self._check, self._world, self._rank = lib, _C._check, world, rank
         self.exchange = "p2p"
         dist.barrier(group=group)
-        # self-test on the live mapping (the bucket content is scratch at this point): ones must sum to `world` everywhere
+        # self-test on the live mapping: ones must sum to `world` in every bucket
         self.flat.fill_(1.0)
         self.all_reduce(group=group)
-        torch.cuda.synchronize(self.flat.device)
+        torch.cuda.synchronize(dev)
         good = bool((self.flat == float(world)).all().item())
         self.flat.zero_()
         if not good:

@@ -178,6 +178,12 @@ GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, 
 /* Enables peer access from the current device to `peer_device` (needed once per peer before kernels of this device
  * may dereference that peer's IPC-mapped memory).  Idempotent. */
 GOF_API int gof_enable_peer_access(int peer_device);
+/* Buffers for that exchange: gof_peer_alloc = cudaMalloc'ed, zero-filled buffer + its 64-byte CUDA IPC handle;
+ * gof_peer_open maps a peer's buffer (handle received from that process) for the CURRENT device. */
+GOF_API int gof_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+GOF_API int gof_peer_open(const unsigned char* handle64, void** ptr);
+GOF_API int gof_peer_close(void* ptr);
+GOF_API int gof_peer_free(void* ptr);
 
 GOF_API const char* gof_last_error(void);
 GOF_API int gof_version(void);
