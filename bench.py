@@ -174,7 +174,7 @@ def run_ours(args, rank, world, dev):
     wl = Workload(args.config, dev, rank, world)
     bucket = gof_dp.GradBucket(wl.P, 16, dev)
     exchange_note = None
-    if world > 1 and args.exchange == "p2p":
+    if world > 1 and (args.exchange == "p2p" or (args.exchange == "auto" and world in (2, 4))):
         try:
             bucket.enable_peer_exchange()
         except Exception as e:   # e.g. no peer access between the GPUs of this box: say so and use NCCL
@@ -482,8 +482,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(gof_synth.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
-                    help="N>1: gradient exchange by NCCL's all-reduce (default) or the library's NVLink peer-memory kernel")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1 gradient exchange: the library's NVLink peer-memory kernel (p2p), NCCL's all-reduce (nccl), or auto = p2p for the world sizes it has been validated on (2 and 4), NCCL otherwise")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():
