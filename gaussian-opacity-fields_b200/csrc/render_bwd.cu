@@ -35,12 +35,6 @@ struct BwdArgs {
 
 constexpr int BATCH = GOF_BLOCK_SIZE;
 
-__device__ __forceinline__ bool box_hits(uint32_t lo, uint32_t hi, int wx0, int wy0, int wx1, int wy1) {
-  const int x0 = (int)(short)(lo & 0xffffu), y0 = (int)(short)(lo >> 16);
-  const int x1 = (int)(short)(hi & 0xffffu), y1 = (int)(short)(hi >> 16);
-  return x0 <= wx1 && x1 >= wx0 && y0 <= wy1 && y1 >= wy0;
-}
-
 // Sum 16 per-lane values over the warp with 16 shuffles (instead of 16 x 5): at every step each lane keeps half of
 // its values and trades the other half with its partner.  On return `r` holds, in BOTH lanes of each even/odd
 // pair, the warp-wide sum of value number (lane >> 1).
