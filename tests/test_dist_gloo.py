@@ -80,3 +80,22 @@ def test_bucket_single_process_noop():
     assert float(b.flat.sum()) == 10 * 48
     b.zero_()
     assert float(b.flat.abs().sum()) == 0.0
+
+
+def test_bucket_layout_and_padding():
+    """The flat buffer is padded to float4 granularity (peer-exchange kernel), views tile its first 59*P floats in the
+    documented order, and the peer exchange is a no-op without a process group."""
+    import gof_dp
+    for P in (1, 3, 10, 1001):
+        b = gof_dp.GradBucket(P, 16, "cpu")
+        assert b.numel == 59 * P and b.flat.numel() % 4 == 0 and 0 <= b.flat.numel() - b.numel < 4
+        off = 0
+        for name, per in (("dmeans3D", 3), ("dsh", 48), ("dopacity", 1), ("dscales", 3), ("drot", 4)):
+            v = b.views[name]
+            assert v.numel() == per * P and v.is_contiguous()
+            assert v.data_ptr() == b.flat.data_ptr() + 4 * off, name
+            off += v.numel()
+        b.views["dsh"].fill_(2.0)
+        assert float(b.flat.sum()) == 2.0 * 48 * P
+        assert b.enable_peer_exchange() is b and b.exchange == "nccl"
+        assert b.all_reduce() is None
