@@ -185,6 +185,17 @@ GOF_API int gof_peer_open(const unsigned char* handle64, void** ptr);
 GOF_API int gof_peer_close(void* ptr);
 GOF_API int gof_peer_free(void* ptr);
 
+/* The per-view training loss on the 9-channel render and its gradient (reference: train.py:151-188,
+ * utils/loss_utils.py:17-63, utils/depth_utils.py:6-35; SURVEY.md 8(f) rank 1 -- a caller of the rasterizer, not part
+ * of its drop-in surface):  loss = (1-l)*L1(rgb,gt) + l*(1-SSIM(rgb,gt)) + l_dn*mean(1 - n_world.n_depth) + l_dist*mean(ch 8).
+ * Device pointers: render [9,H,W], gt [3,H,W], terms [5] = (L1, SSIM, normal loss, distortion loss, total),
+ * grad [9,H,W] = d total / d render (NULL: values only), scratch of gof_view_loss_scratch_bytes(W,H) bytes.
+ * c2w_R9 is a HOST pointer to the row-major camera-to-world rotation ((world_view_transform^T)^-1 [:3,:3]). */
+GOF_API size_t gof_view_loss_scratch_bytes(int W, int H);
+GOF_API int gof_view_loss(int W, int H, const float* render, const float* gt, const float* c2w_R9, float fx, float fy,
+                          float lambda_dssim, float lambda_depth_normal, float lambda_distortion, float* terms,
+                          float* grad, void* scratch, void* stream);
+
 GOF_API const char* gof_last_error(void);
 GOF_API int gof_version(void);
 
