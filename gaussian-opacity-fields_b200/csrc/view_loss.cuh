@@ -6,7 +6,7 @@
 // STAGED COMPONENT: not on the rasterizer's drop-in path.  The work of one 16x16 pixel tile is
 // written as PHASES -- device functions of (tile, thread id, shared block) separated by block barriers -- so that
 // tests/hostmath can compile this very file for the host, run the phases thread by thread, and check the result against
-// the CPU oracle (oracle/loss_oracle.py, pinned to the reference's own Python) without a GPU.
+// an independent CPU restatement pinned to the reference's own Python, without a GPU.
 //
 //   kernel A (vl_a_*):  SSIM statistics of the tile (11x11 window, zero padding) -> SSIM map sum, L1 sum, and the three
 //                       derivative maps d map/d(mu1, E11, E12) for kernel B; depth -> normal on a 2-pixel halo, normal
