@@ -8,7 +8,9 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# Staged component: its CUDA wrapper has not been run on a GPU yet (the kernel SOURCE is verified on the CPU, phase by phase,
+# in test_view_loss_host.py).  Opt in with GOF_STAGED=1 until that first run has happened.
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GOF_STAGED") != "1", reason="staged: set GOF_STAGED=1")]
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIX = sorted(glob.glob(os.path.join(HERE, "golden", "loss_*.npz")))
 
