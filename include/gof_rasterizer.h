@@ -196,6 +196,21 @@ GOF_API int gof_view_loss(int W, int H, const float* render, const float* gt, co
                           float lambda_dssim, float lambda_depth_normal, float lambda_distortion, float* terms,
                           float* grad, void* scratch, void* stream);
 
+/* Parameter prologue / epilogue around the rasterizer (callers of the rasterizer, staged):
+ * activations with the 3D filter (scene/gaussian_model.py:152-194: scales = sqrt(exp(s)^2 + f^2), rotations = normalize(q),
+ * opacity = sigmoid(o) * sqrt(prod exp(s)^2 / prod(exp(s)^2 + f^2)), shs = cat(f_dc, f_rest)), their backward (raw-parameter
+ * gradients from the rasterizer's output gradients), and one torch.optim.Adam step (:360, eps 1e-15).  Device pointers, fp32. */
+GOF_API int gof_activate_params(int P, int M_rest, const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                                const float* filter_3D, const float* features_dc, const float* features_rest, float* scales,
+                                float* rotations, float* opacities, float* shs, void* stream);
+GOF_API int gof_activate_params_backward(int P, int M_rest, const float* scaling_raw, const float* rotation_raw,
+                                         const float* opacity_raw, const float* filter_3D, const float* g_scales,
+                                         const float* g_rotations, const float* g_opacities, const float* g_shs,
+                                         float* d_scaling_raw, float* d_rotation_raw, float* d_opacity_raw,
+                                         float* d_features_dc, float* d_features_rest, void* stream);
+GOF_API int gof_adam_step(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, double lr, double beta1,
+                          double beta2, double eps, int step, void* stream);
+
 GOF_API const char* gof_last_error(void);
 GOF_API int gof_version(void);
 
