@@ -1,0 +1,59 @@
+// filter3d.cu -- kernels and C ABI of compute_3D_filter (see filter3d.cuh; scene/gaussian_model.py:262-311).  STAGED:
+// the per-point arithmetic is verified on the CPU (tests/test_filter3d_host.py); this wrapper has not run on a GPU yet.
+// Pass 1: per point the minimal valid depth over all cameras (one thread per point, camera table read through the
+// read-only path) and the maximum of the seen depths (block reduction + atomicMax on the float's bit pattern: depths are
+// positive).  Pass 2: unseen points take that maximum; filter = distance / max focal * sqrt(0.2).
+#include <math.h>
+
+#include "filter3d.cuh"
+#include "gof_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_filter3d_min(int P, const float* __restrict__ xyz, int n_cams, const float* __restrict__ cams,
+                                                      float* __restrict__ dist, unsigned int* __restrict__ dmax_bits) {
+  __shared__ float s_max[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float mine = 0.0f;                                   // seen depths are > 0.2
+  if (i < P) {
+    const float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    bool seen;
+    const float d = f3_min_depth(p, cams, n_cams, &seen);
+    dist[i] = seen ? d : -1.0f;
+    if (seen) mine = d;
+  }
+  s_max[threadIdx.x] = mine;
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+    __syncthreads();
+    if ((int)threadIdx.x < stride) s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + stride]);
+  }
+  if (threadIdx.x == 0 && s_max[0] > 0.0f) atomicMax(dmax_bits, __float_as_uint(s_max[0]));   // positive floats order like uints
+}
+
+__global__ void __launch_bounds__(256) k_filter3d_fill(int P, float* __restrict__ dist, const unsigned int* __restrict__ dmax_bits,
+                                                       float inv_focal_k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float d = dist[i];
+  dist[i] = (d < 0.0f ? __uint_as_float(*dmax_bits) : d) * inv_focal_k;
+}
+
+}  // namespace
+
+// xyz [P,3], cams [n_cams,16] = (R 3x3 as stored by the reference, T, focal_x, focal_y, width, height), filter_3D [P] out,
+// scratch: 4 bytes; all device pointers except max_focal (host value = largest focal_x of the cameras).
+extern "C" GOF_API int gof_compute_3d_filter(int P, const float* xyz, int n_cams, const float* cams, float max_focal, float* filter_3D,
+                                             void* scratch4, void* stream) {
+  if (P < 0 || n_cams < 0) { gof_set_error("compute_3d_filter: bad sizes"); return GOF_E_INVALID; }
+  if (P == 0) return GOF_OK;
+  if (!xyz || (n_cams > 0 && !cams) || !filter_3D || !scratch4 || !(max_focal > 0.f)) { gof_set_error("compute_3d_filter: bad arguments"); return GOF_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* dmax = static_cast<unsigned int*>(scratch4);
+  GOF_CUDA_OK(cudaMemsetAsync(dmax, 0, 4, st));
+  const unsigned blocks = (unsigned)((P + 255) / 256);
+  GOF_LAUNCH("filter3d_min", st, k_filter3d_min<<<blocks, 256, 0, st>>>(P, xyz, n_cams, cams, filter_3D, dmax));
+  GOF_LAUNCH_CHECK(false, st);
+  GOF_LAUNCH("filter3d_fill", st, k_filter3d_fill<<<blocks, 256, 0, st>>>(P, filter_3D, dmax, sqrtf(0.2f) / max_focal));
+  GOF_LAUNCH_CHECK(false, st);
+  return GOF_OK;
+}

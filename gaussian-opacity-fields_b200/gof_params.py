@@ -76,3 +76,30 @@ def adam_step(param, exp_avg, exp_avg_sq, grad, lr, step, beta1=0.9, beta2=0.999
         _C._check(_lib.gof_adam_step(param.numel(), param.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), grad.data_ptr(),
                                      float(lr), float(beta1), float(beta2), float(eps), int(step), _C._stream()))
     return param
+
+
+_lib.gof_compute_3d_filter.restype = ctypes.c_int
+_lib.gof_compute_3d_filter.argtypes = [ctypes.c_int, _v, ctypes.c_int, _v, ctypes.c_float, _v, _v, _v]
+
+
+def pack_cameras(cameras, device):
+    """[n,16] float32 table for compute_3d_filter from objects with the reference Camera's attributes
+    (R, T, focal_x, focal_y, image_width, image_height; scene/cameras.py)."""
+    rows = []
+    for c in cameras:
+        rows.append(torch.cat([torch.as_tensor(c.R, dtype=torch.float32).reshape(-1), torch.as_tensor(c.T, dtype=torch.float32).reshape(-1),
+                               torch.tensor([c.focal_x, c.focal_y, c.image_width, c.image_height], dtype=torch.float32)]))
+    return torch.stack(rows).contiguous().to(device)
+
+
+@torch.no_grad()
+def compute_3d_filter(xyz, cam_table, max_focal):
+    """== GaussianModel.compute_3D_filter (scene/gaussian_model.py:262-311): returns filter_3D [P,1]."""
+    x = _f32(xyz)
+    P = int(x.shape[0])
+    out = torch.empty(P, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(1, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _C._check(_lib.gof_compute_3d_filter(P, x.data_ptr(), int(cam_table.shape[0]), _f32(cam_table).data_ptr(), float(max_focal),
+                                             out.data_ptr(), scratch.data_ptr(), _C._stream()))
+    return out[:, None]

@@ -208,6 +208,12 @@ GOF_API int gof_activate_params_backward(int P, int M_rest, const float* scaling
                                          const float* g_rotations, const float* g_opacities, const float* g_shs,
                                          float* d_scaling_raw, float* d_rotation_raw, float* d_opacity_raw,
                                          float* d_features_dc, float* d_features_rest, void* stream);
+/* GaussianModel.compute_3D_filter (scene/gaussian_model.py:262-311; staged): per point the smallest camera-space depth over the
+ * cameras that see it (depth > 0.2, projection inside the image enlarged by 15 %), unseen points take the largest seen
+ * depth; filter = depth / max_focal * sqrt(0.2).  cams [n_cams,16] = R (3x3 as the reference stores it, used as xyz @ R),
+ * T, focal_x, focal_y, width, height.  scratch4: 4 device bytes. */
+GOF_API int gof_compute_3d_filter(int P, const float* xyz, int n_cams, const float* cams, float max_focal, float* filter_3D,
+                                  void* scratch4, void* stream);
 GOF_API int gof_adam_step(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, double lr, double beta1,
                           double beta2, double eps, int step, void* stream);
 

@@ -42,3 +42,14 @@ def test_activate_and_adam(path):
         gof_params.adam_step(p, m, v, torch.from_numpy(g).to(dev).contiguous(), float(fx["adam_lr"]), step)
     assert _rel(m.cpu().numpy(), fx["adam_m"]) < 1e-6 and _rel(v.cpu().numpy(), fx["adam_v"]) < 1e-6
     assert float(np.abs(p.cpu().numpy() - fx["adam_p"]).max()) < 1e-6
+
+
+def test_compute_3d_filter():
+    import gof_params
+    fx = np.load(os.path.join(HERE, "golden", "filter3d_a.npz"))
+    dev = torch.device("cuda")
+    cams = torch.from_numpy(fx["cams"]).to(dev)
+    out = gof_params.compute_3d_filter(torch.from_numpy(fx["xyz"]).to(dev), cams, float(fx["cams"][:, 12].max()))
+    ref = fx["filter_3D"]
+    rel = np.abs(out.cpu().numpy() - ref) / ref
+    assert np.quantile(rel, 0.999) < 1e-5 and (rel > 1e-5).sum() <= 3
