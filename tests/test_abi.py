@@ -120,3 +120,15 @@ def test_scratch_buffers_die_by_refcount_not_by_gc():
         assert w() is None, "scratch tensor kept alive by a reference cycle"
     finally:
         gc.enable()
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/gof_rasterizer.h is the C-ABI contract: it must compile as C99 (no torch, no C++) and as C++."""
+    import subprocess
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include")
+    c = tmp_path / "h.c"
+    c.write_text('#include "gof_rasterizer.h"\nint main(void) { return gof_version() == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-c", str(c), "-o", str(tmp_path / "h.o")])
+    cpp = tmp_path / "h.cpp"
+    cpp.write_text('#include "gof_rasterizer.h"\nint main() { return gof_version() == 0; }\n')
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Werror", "-I", inc, "-c", str(cpp), "-o", str(tmp_path / "h2.o")])
