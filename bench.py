@@ -229,6 +229,17 @@ def run_ours(args, rank, world, dev):
     V = int((stats["V"] > 0).sum())
     R = int(stats["R"])
     N = wl.W * wl.H
+    # tile-list statistics of the last view (one extra, untimed forward; omitted if anything goes wrong)
+    tile_stats = {}
+    try:
+        fa = wl.fwd_args(wl.view(args.warmup))
+        R2, _c, radii2, geom2, bin2, img2 = _C.rasterize_gaussians(*fa)
+        st2 = _C.export_state(wl.P, wl.W, wl.H, R2, geom2, bin2, img2, radii2)
+        lens = (st2["ranges"][:, 1] - st2["ranges"][:, 0]).to(torch.float64)
+        tile_stats = {"tile_list_mean": float(lens.mean()), "tile_list_max": int(lens.max())}
+        del st2, geom2, bin2, img2
+    except Exception:
+        tile_stats = {}
 
     # ---- end to end through the public API with host inputs ---------------------------------------------------
     params = {k: wl.gs[k].detach().clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
@@ -329,7 +340,7 @@ def run_ours(args, rank, world, dev):
         "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {wl.P} Gaussians, {wl.W}x{wl.H}, sh_degree 3, seed {wl.cfg['seed']}, "
-                               f"64-view ring, 1 view/step/GPU", "visible": V, "num_rendered": R,
+                               f"64-view ring, 1 view/step/GPU", "visible": V, "num_rendered": R, **tile_stats,
                    "parallelism": f"view-parallel dp{world}" if world > 1 else "single GPU",
                    "l2": "no explicit flush: a step touches >400 MB (> 126 MB L2) and every step renders a new view"},
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d,
