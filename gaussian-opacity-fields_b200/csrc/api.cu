@@ -384,7 +384,7 @@ extern "C" int gof_integrate(const gof_scene_t* s, int PN, const float* points3D
   uint32_t R = 0;
   if ((rc = gof_read_back(&R, geom + GL.total, sizeof(uint32_t), st)) != GOF_OK) return rc;
   *num_rendered = (int)R;
-  const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height);
+  const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height, /*with_masks=*/false);
   char* bin = (char*)binning_alloc(binning_user, BL.bytes);
   if (!bin && BL.bytes) { gof_set_error("binning allocator returned NULL"); return GOF_E_ALLOC; }
   if ((rc = gof_bin_tiles(s->P, (size_t)R, v, geom, GL, bin, BL, img, IL, s->debug != 0, st)) != GOF_OK) return rc;

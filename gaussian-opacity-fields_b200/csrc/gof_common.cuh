@@ -211,7 +211,8 @@ static inline int gof_bits_for(uint32_t n) {   // bits needed to represent value
   return b < 1 ? 1 : b;
 }
 
-static inline GofBinLayout gof_bin_layout(size_t R, int W, int H) {
+// with_masks = false: the opacity-field query has no backward, its binning buffer carries no blend masks
+static inline GofBinLayout gof_bin_layout(size_t R, int W, int H, bool with_masks = true) {
   const uint32_t tiles = (uint32_t)((W + 15) / 16) * (uint32_t)((H + 15) / 16);
   GofBinLayout L;
   const int nbits = gof_bits_for(tiles);
@@ -234,7 +235,7 @@ static inline GofBinLayout gof_bin_layout(size_t R, int W, int H) {
   L.point_list = (L.passes % 2 == 0) ? L.val_a : L.val_b;
   L.sorted_keys = (L.passes % 2 == 0) ? L.key_a : L.key_b;
   L.vmask_stride = R + 32 * (size_t)tiles;
-  L.vmask = take(L.vmask_stride * 32);
+  L.vmask = with_masks ? take(L.vmask_stride * 32) : o;
   L.bytes = o;
   return L;
 }
