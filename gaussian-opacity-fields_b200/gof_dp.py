@@ -62,20 +62,38 @@ class GradBucket:
         lib.gof_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]
         lib.gof_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
         lib.gof_p2p_allreduce_sum_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        def agree(ok):   # True only if every rank says so: all ranks leave this function the same way (raise or return)
+            t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return float(t.item()) == 1.0
+
         ptr, handle = ctypes.c_void_p(0), ctypes.create_string_buffer(64)
+        err = None
         with torch.cuda.device(dev):
             torch.cuda.synchronize()
-            _C._check(lib.gof_peer_alloc(n * 4, ctypes.byref(ptr), handle))
+            try:
+                _C._check(lib.gof_peer_alloc(n * 4, ctypes.byref(ptr), handle))
+                mine = bytes(handle.raw)
+            except Exception as e:   # noqa: BLE001 -- reported below, on every rank
+                err, mine = e, None
             handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            dist.all_gather_object(handles, mine, group=group)
             ptrs = []
-            for r in range(world):
-                if r == rank:
-                    ptrs.append(ptr.value)
-                else:
-                    q = ctypes.c_void_p(0)
-                    _C._check(lib.gof_peer_open(handles[r], ctypes.byref(q)))
-                    ptrs.append(q.value)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for r in range(world):
+                        if r == rank:
+                            ptrs.append(ptr.value)
+                        else:
+                            q = ctypes.c_void_p(0)
+                            _C._check(lib.gof_peer_open(handles[r], ctypes.byref(q)))
+                            ptrs.append(q.value)
+                except Exception as e:   # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("a peer could not allocate its shareable bucket")
+        if not agree(err is None):
+            raise RuntimeError(f"peer exchange: mapping failed on some rank ({err if err is not None else 'another rank'})")
 
         class _Raw:   # zero-copy torch view of the cudaMalloc'ed bucket
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
@@ -97,11 +115,11 @@ class GradBucket:
         self.flat.fill_(1.0)
         self.all_reduce(group=group)
         torch.cuda.synchronize(dev)
-        good = bool((self.flat == float(world)).all().item())
+        good = agree(bool((self.flat == float(world)).all().item()))
         self.flat.zero_()
         if not good:
             self.exchange = "nccl"
-            raise RuntimeError("peer exchange self-test failed")
+            raise RuntimeError("peer exchange self-test failed on some rank")
         return self
 
     def all_reduce(self, group=None, async_op=False):
