@@ -97,3 +97,33 @@ def test_sh_layouts_against_live_reference(ref, M, deg):
     # coefficients above the active degree receive no gradient (backward.cu:20-139 writes degree <= D only)
     used = (deg + 1) ** 2
     assert float(go[5][:, used:, :].abs().max()) == 0.0 if used < M else True
+
+
+@pytest.mark.skipif(__import__("os").environ.get("GOF_STAGED") != "1",
+                    reason="coverage gap found at the end of round 1, first GPU run pending: set GOF_STAGED=1")
+def test_view2gaussian_precomp_against_live_reference(ref):
+    """`view2gaussian_precomp` supplied by the caller (gaussian_renderer/__init__.py: pipe.compute_view2gaussian_python):
+    K1 must take the 10-float records as given, the backward must return dL_dview2gaussian and leave scale/rotation
+    gradients to the caller's autograd."""
+    from diff_gaussian_rasterization import _C as ours
+    dev = torch.device("cuda")
+    cam, gs = gof_synth.make_scene(dict(P=50_000, width=640, height=400, seed=31), view=5)
+    fa = list(_util.fwd_args(cam, gs, dev))
+    P, W, H = 50_000, 640, 400
+    R0, c0, rad0, geo0, bin0, im0 = ours.rasterize_gaussians(*fa)
+    v2g = ours.export_state(P, W, H, R0, geo0, bin0, im0, rad0)["view2gaussian"].contiguous()   # bit-exact to the reference's
+    fa[8] = v2g                                                                                 # view2gaussian_precomp
+    fa = tuple(fa)
+    Ro, co, rado, geo, bino, imo = ours.rasterize_gaussians(*fa)
+    Rr, cr, radr, ger, binr, imr = ref.rasterize_gaussians(*fa)
+    assert Ro == Rr and torch.equal(rado, radr)
+    for ch in range(9):
+        assert _util.rel_err(co[ch], cr[ch])[0] < (2e-5 if ch == 8 else 2e-6), f"channel {ch}"
+    assert torch.equal(co[6], c0[6]) and torch.equal(co[7], c0[7])          # same records -> same image as the computed path
+    grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(4)).to(dev)
+    go = ours.rasterize_gaussians_backward(*_util.bwd_args(fa, rado, geo, Ro, bino, imo, grad))
+    g1 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    g2 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    for n, a, b, c in zip(NAMES, go, g1, g2):
+        noise = _util.rel_err(c, b)[0]
+        assert _util.rel_err(a, b)[0] <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {_util.rel_err(a, b)[0]}, ref-vs-ref {noise}"
