@@ -1,8 +1,10 @@
-// filter3d.cu -- kernels and C ABI of compute_3D_filter (see filter3d.cuh; scene/gaussian_model.py:262-311).  STAGED:
-// the per-point arithmetic is verified on the CPU (tests/test_filter3d_host.py); this wrapper has not run on a GPU yet.
+// filter3d.cu -- kernels and C ABI of compute_3D_filter (see filter3d.cuh; scene/gaussian_model.py:262-311).
+// The per-point arithmetic is verified on the CPU (tests/test_filter3d_host.py), the wrapper by tests/test_gpu_param_ops.py.
 // Pass 1: per point the minimal valid depth over all cameras (one thread per point, camera table read through the
 // read-only path) and the maximum of the seen depths (block reduction + atomicMax on the float's bit pattern: depths are
-// positive).  Pass 2: unseen points take that maximum; filter = distance / max focal * sqrt(0.2).
+// positive).  Pass 2: unseen points take that maximum; filter = distance / max focal * sqrt(0.2) in the reference's order
+// (:306: float division by the focal length, then the float product with 0.2 ** 0.5).  When NO point is seen the reference
+// raises (max() of an empty tensor, :301); here *scratch4 stays 0 and the caller must treat that as the error.
 #include <math.h>
 
 #include "filter3d.cuh"
@@ -31,11 +33,11 @@ __global__ void __launch_bounds__(256) k_filter3d_min(int P, const float* __rest
 }
 
 __global__ void __launch_bounds__(256) k_filter3d_fill(int P, float* __restrict__ dist, const unsigned int* __restrict__ dmax_bits,
-                                                       float inv_focal_k) {
+                                                       float max_focal) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const float d = dist[i];
-  dist[i] = (d < 0.0f ? __uint_as_float(*dmax_bits) : d) * inv_focal_k;
+  dist[i] = __fmul_rn(__fdiv_rn(d < 0.0f ? __uint_as_float(*dmax_bits) : d, max_focal), 0.4472135954999579f);
 }
 
 }  // namespace
@@ -53,7 +55,7 @@ extern "C" GOF_API int gof_compute_3d_filter(int P, const float* xyz, int n_cams
   const unsigned blocks = (unsigned)((P + 255) / 256);
   GOF_LAUNCH("filter3d_min", st, k_filter3d_min<<<blocks, 256, 0, st>>>(P, xyz, n_cams, cams, filter_3D, dmax));
   GOF_LAUNCH_CHECK(false, st);
-  GOF_LAUNCH("filter3d_fill", st, k_filter3d_fill<<<blocks, 256, 0, st>>>(P, filter_3D, dmax, sqrtf(0.2f) / max_focal));
+  GOF_LAUNCH("filter3d_fill", st, k_filter3d_fill<<<blocks, 256, 0, st>>>(P, filter_3D, dmax, max_focal));
   GOF_LAUNCH_CHECK(false, st);
   return GOF_OK;
 }

@@ -82,10 +82,15 @@ def _ptr(t, dtype=torch.float32, device=None):
 
 
 def _c(t, dtype=torch.float32):
-    """contiguous (keeps a reference alive in the caller's frame)"""
+    """contiguous and 16-byte aligned (keeps a reference alive in the caller's frame).  The kernels read rotations as float4
+    and SH rows with 128-bit loads; the reference accepts any 4-byte aligned tensor, so a contiguous view with an odd storage
+    offset (a parameter sliced out of a flat buffer) is copied to a fresh allocation instead of faulting."""
     if t is None:
         return None
-    return t.contiguous()
+    t = t.contiguous()
+    if t.is_cuda and t.numel() and (t.data_ptr() & 15):
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
 
 
 class _Pool:
@@ -256,7 +261,10 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         # of one flat all-reduce buffer, so the backward writes straight into the communication buffer
         if _out is not None and name in _out:
             t = _out[name]
-            assert t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.dtype == means3D.dtype
+            if not (t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.dtype == means3D.dtype):
+                raise RuntimeError(f"gof_b200: _out[{name!r}] must be a contiguous {means3D.dtype} tensor of shape {tuple(shape)}")
+            if t.numel() and (t.data_ptr() & 15):
+                raise RuntimeError(f"gof_b200: _out[{name!r}] must be 16-byte aligned (128-bit stores)")
             return t
         n = 1
         for d in shape:

@@ -27,19 +27,23 @@ class GradBucket:
         shapes = {}
         for name, tail in _FIELDS:
             shapes[name] = (self.P, self.M, 3) if name == "dsh" else (self.P,) + tail
-        self.numel = sum(int(torch.Size(s).numel()) for s in shapes.values())
-        self.flat = torch.zeros((self.numel + 3) // 4 * 4, dtype=dtype, device=device)   # float4 granularity for the peer kernel
-        self.views = {}
-        off = 0
+        # Every field starts on a 256-byte boundary: k_preprocess_backward stores dL_drot as float4 and dL_dsh as
+        # 128-bit rows, so the views must be 16-byte aligned for ANY P (after densification P is arbitrary).
+        self._offsets, off = {}, 0
         for name, shape in shapes.items():
-            n = int(torch.Size(shape).numel())
-            self.views[name] = self.flat[off:off + n].view(shape)
-            off += n
+            self._offsets[name] = (off, shape)
+            off += (int(torch.Size(shape).numel()) + 63) // 64 * 64
+        self.numel = off
+        self.flat = torch.zeros(max(self.numel, 64), dtype=dtype, device=device)
+        self.views = self._make_views()
 
-        self._peers = None       # tensors mapping every rank's flat buffer (CUDA IPC), index = rank
-        self._peer_ptrs = None
+        self._peer_ptrs = None   # addresses (this process) of every rank's bucket, index = rank; own cudaMalloc at [rank]
+        self._own_ptr, self._mapped = None, []
         self._sync = None
         self.exchange = "nccl"
+
+    def _make_views(self):
+        return {name: self.flat[off:off + int(torch.Size(shape).numel())].view(shape) for name, (off, shape) in self._offsets.items()}
 
     def zero_(self):
         self.flat.zero_()
@@ -92,20 +96,20 @@ class GradBucket:
                     err = e
             elif err is None:
                 err = RuntimeError("a peer could not allocate its shareable bucket")
+        self._lib = lib
+        self._own_ptr = ptr.value
+        self._mapped = [q for r, q in enumerate(ptrs) if r != rank]
         if not agree(err is None):
+            self._release_peer_memory()
             raise RuntimeError(f"peer exchange: mapping failed on some rank ({err if err is not None else 'another rank'})")
 
         class _Raw:   # zero-copy torch view of the cudaMalloc'ed bucket
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
         self._raw = _Raw()
-        old_views = self.views
         self.flat = torch.as_tensor(self._raw, device=dev)
         if self.flat.data_ptr() != ptr.value or self.flat.numel() != n:
             raise RuntimeError("peer exchange: could not wrap the shared allocation")
-        self.views, off = {}, 0
-        for name, v in old_views.items():
-            self.views[name] = self.flat[off:off + v.numel()].view(v.shape)
-            off += v.numel()
+        self.views = self._make_views()
         self._peer_ptrs = (ctypes.c_void_p * world)(*ptrs)
         self._sync = torch.zeros(1, dtype=torch.float32, device=dev)
         self._lib, self._check, self._world, self._rank = lib, _C._check, world, rank
@@ -118,15 +122,57 @@ class GradBucket:
         good = agree(bool((self.flat == float(world)).all().item()))
         self.flat.zero_()
         if not good:
-            self.exchange = "nccl"
+            self.close()
             raise RuntimeError("peer exchange self-test failed on some rank")
         return self
+
+    def _release_peer_memory(self):
+        lib = getattr(self, "_lib", None)
+        if lib is None:
+            return
+        lib.gof_peer_close.argtypes = [ctypes.c_void_p]
+        lib.gof_peer_free.argtypes = [ctypes.c_void_p]
+        for q in self._mapped:
+            if q:
+                lib.gof_peer_close(ctypes.c_void_p(q))
+        self._mapped = []
+        if self._own_ptr:
+            lib.gof_peer_free(ctypes.c_void_p(self._own_ptr))
+        self._own_ptr = None
+
+    def close(self, group=None):
+        """Leaves peer-exchange mode: unmaps the peers' buckets, frees the shared allocation and falls back to a torch-owned
+        buffer + NCCL.  Collective when peer exchange was enabled (every rank must stop using its peers' memory first).
+        The views are re-created (their contents are not kept)."""
+        if self.exchange != "p2p" and not self._own_ptr:
+            return
+        dev = self.flat.device
+        if dist.is_available() and dist.is_initialized():
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)
+        self.exchange = "nccl"
+        n = self.flat.numel()
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = self._make_views()
+        self._raw, self._peer_ptrs = None, None
+        self._release_peer_memory()
+
+    def __del__(self):
+        # non-collective last resort (interpreter teardown / bucket re-created after densification without close()):
+        # the mappings and the allocation are released; peers that still map this bucket keep it alive in the driver
+        try:
+            self._release_peer_memory()
+        except Exception:   # noqa: BLE001
+            pass
 
     def all_reduce(self, group=None, async_op=False):
         """Sum over ranks.  World size 1: no-op."""
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
         if self.exchange == "p2p":
+            if async_op:
+                raise ValueError("GradBucket.all_reduce(async_op=True) is not available with the peer-memory exchange: "
+                                 "the kernel is ordered on the current stream")
             # barrier: every rank's backward has filled its bucket (a 4-byte NCCL all-reduce on the same stream orders it
             # after the local kernels and completes only when every rank has reached it)
             dist.all_reduce(self._sync, group=group)

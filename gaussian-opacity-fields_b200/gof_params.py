@@ -1,7 +1,7 @@
 """Parameter prologue / epilogue around the rasterizer (reference:
 scene/gaussian_model.py:152-194 and :360) through the C ABI (`gof_activate_params*`, `gof_adam_step`, csrc/param_ops.cu).
 STAGED: the arithmetic is verified on the CPU against goldens generated from the reference's Python
-(tests/test_param_ops_host.py); the CUDA wrappers are exercised by tests/test_gpu_param_ops.py (opt-in, GOF_STAGED=1).
+(tests/test_param_ops_host.py); the CUDA wrappers are exercised by tests/test_gpu_param_ops.py.
 
     scales, rotations, opacities, shs = activate(_scaling, _rotation, _opacity, filter_3D, _features_dc, _features_rest)
         == (pc.get_scaling_with_3D_filter, pc.get_rotation, pc.get_opacity_with_3D_filter, pc.get_features), differentiable
@@ -102,4 +102,7 @@ def compute_3d_filter(xyz, cam_table, max_focal):
     with torch.cuda.device(x.device):
         _C._check(_lib.gof_compute_3d_filter(P, x.data_ptr(), int(cam_table.shape[0]), _f32(cam_table).data_ptr(), float(max_focal),
                                              out.data_ptr(), scratch.data_ptr(), _C._stream()))
+    # the reference raises here too (distance[valid_points].max() of an empty tensor, :301) -- and synchronises, like this read
+    if P and int(scratch.item()) == 0:
+        raise RuntimeError("compute_3D_filter: no point is seen by any camera")
     return out[:, None]

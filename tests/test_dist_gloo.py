@@ -25,7 +25,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     P, M = 257, 16
     b = gof_dp.GradBucket(P, M, "cpu")
-    assert b.numel == P * 59
+    assert sum(v.numel() for v in b.views.values()) == P * 59
     g = torch.Generator().manual_seed(rank)
     local = {}
     for name, v in b.views.items():
@@ -83,19 +83,22 @@ def test_bucket_single_process_noop():
 
 
 def test_bucket_layout_and_padding():
-    """The flat buffer is padded to float4 granularity (peer-exchange kernel), views tile its first 59*P floats in the
-    documented order, and the peer exchange is a no-op without a process group."""
+    """Views appear in the documented order, every one starts on a 256-byte boundary for ANY P (k_preprocess_backward stores
+    dL_drot / dL_dsh with 128-bit stores), the padding is never written, and the peer exchange is a no-op without a group."""
     import gof_dp
-    for P in (1, 3, 10, 1001):
+    for P in (1, 3, 10, 1001, 100_003):
         b = gof_dp.GradBucket(P, 16, "cpu")
-        assert b.numel == 59 * P and b.flat.numel() % 4 == 0 and 0 <= b.flat.numel() - b.numel < 4
-        off = 0
+        assert b.flat.numel() % 64 == 0 and b.flat.numel() == b.numel
+        last = -1
         for name, per in (("dmeans3D", 3), ("dsh", 48), ("dopacity", 1), ("dscales", 3), ("drot", 4)):
             v = b.views[name]
+            off = (v.data_ptr() - b.flat.data_ptr()) // 4
             assert v.numel() == per * P and v.is_contiguous()
-            assert v.data_ptr() == b.flat.data_ptr() + 4 * off, name
-            off += v.numel()
+            assert off % 64 == 0 and off > last, name
+            last = off + v.numel() - 1
+        assert last < b.flat.numel()
         b.views["dsh"].fill_(2.0)
         assert float(b.flat.sum()) == 2.0 * 48 * P
         assert b.enable_peer_exchange() is b and b.exchange == "nccl"
         assert b.all_reduce() is None
+        b.close()                                   # no-op outside peer mode

@@ -99,8 +99,6 @@ def test_sh_layouts_against_live_reference(ref, M, deg):
     assert float(go[5][:, used:, :].abs().max()) == 0.0 if used < M else True
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GOF_STAGED") != "1",
-                    reason="coverage gap found at the end of round 1, first GPU run pending: set GOF_STAGED=1")
 def test_view2gaussian_precomp_against_live_reference(ref):
     """`view2gaussian_precomp` supplied by the caller (gaussian_renderer/__init__.py: pipe.compute_view2gaussian_python):
     K1 must take the 10-float records as given, the backward must return dL_dview2gaussian and leave scale/rotation
@@ -127,3 +125,107 @@ def test_view2gaussian_precomp_against_live_reference(ref):
     for n, a, b, c in zip(NAMES, go, g1, g2):
         noise = _util.rel_err(c, b)[0]
         assert _util.rel_err(a, b)[0] <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {_util.rel_err(a, b)[0]}, ref-vs-ref {noise}"
+
+
+def _cov3d_from(scales, rotations, mod):
+    """computeCov3D (forward.cu:129-163) in torch float64 -> float32: Sigma = (S R)^T (S R), upper triangle."""
+    s = scales.double() * mod
+    r, x, y, z = rotations.double().unbind(1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).view(-1, 3, 3)
+    M = R * s[:, None, :]
+    S = M @ M.transpose(1, 2)
+    return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1).float().contiguous()
+
+
+@pytest.mark.parametrize("with_v2g", [False, True])
+def test_cov3d_precomp_against_live_reference(ref, with_v2g):
+    """`cov3D_precomp` (forward.cu:339-348): the EWA footprint (radii, tiles, 2D conic, coef) comes from the caller's 3D
+    covariance -- here deliberately 1.7x the one scale/rotation would give, so a path that ignored it fails on radii --
+    while view2gaussian comes from scale/rotation (with_v2g=False) or from the caller (with_v2g=True, forward.cu:395-403).
+    The reference dereferences scales/rotations unconditionally (forward.cu:334-335), so they are always supplied here."""
+    from diff_gaussian_rasterization import _C as ours
+    dev = torch.device("cuda")
+    cam, gs = gof_synth.make_scene(dict(P=40_000, width=512, height=384, seed=41), view=9)
+    P, W, H = 40_000, 512, 384
+    fa = list(_util.fwd_args(cam, gs, dev, kernel_size=0.1))
+    fa[7] = _cov3d_from(gs["scales"], gs["rotations"], 1.7).to(dev)       # cov3D_precomp
+    if with_v2g:
+        R0, c0, rad0, geo0, bin0, im0 = ours.rasterize_gaussians(*_util.fwd_args(cam, gs, dev, kernel_size=0.1))
+        v2g = ours.export_state(P, W, H, R0, geo0, bin0, im0, rad0)["view2gaussian"]
+        fa[8] = (v2g * 1.0).contiguous()
+        del geo0, bin0, im0
+    fa = tuple(fa)
+    Ro, co, rado, geo, bino, imo = ours.rasterize_gaussians(*fa)
+    Rr, cr, radr, ger, binr, imr = ref.rasterize_gaussians(*fa)
+    base = ours.rasterize_gaussians(*_util.fwd_args(cam, gs, dev, kernel_size=0.1))
+    assert not torch.equal(base[2], rado), "the inflated covariance must change the radii"
+    assert Ro == Rr and torch.equal(rado, radr)
+    so = ours.export_state(P, W, H, Ro, geo, bino, imo, rado)
+    sg, si, sb = _util.carve_ref_geom(ger, P), _util.carve_ref_image(imr, W, H), _util.carve_ref_binning(binr, Rr)
+    vis = radr > 0
+    assert torch.equal(so["tiles_touched"], sg["tiles_touched"])
+    assert torch.equal(so["point_list"], sb["point_list"])
+    assert torch.equal(so["ranges"], si["ranges"])
+    assert torch.equal(so["n_contrib"], si["n_contrib"])
+    for f in ("depths", "means2D", "conic_opacity"):
+        assert torch.equal(so[f][vis].view(torch.int32), sg[f][vis].view(torch.int32)), f
+    for ch in range(9):
+        assert _util.rel_err(co[ch], cr[ch])[0] < (2e-5 if ch == 8 else 2e-6), f"channel {ch}"
+    grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(6)).to(dev)
+    go = ours.rasterize_gaussians_backward(*_util.bwd_args(fa, rado, geo, Ro, bino, imo, grad))
+    g1 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    g2 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
+    for n, a, b, c in zip(NAMES, go, g1, g2):
+        noise = _util.rel_err(c, b)[0]
+        assert _util.rel_err(a, b)[0] <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {_util.rel_err(a, b)[0]}, ref-vs-ref {noise}"
+    assert float(go[4].abs().max()) == 0.0          # dL_dcov3D stays zero (backward.cu:991-1007: EWA backward disabled)
+
+
+def test_precomp_through_public_api():
+    """GaussianRasterizer.forward(cov3D_precomp=..., view2gaussian_precomp=...) without scales/rotations (the combination the
+    Python surface asks for, dgr.py:206-207): same image and dL_dview2gaussian as the `_C`-level call that also passes
+    scales/rotations.  (The reference itself faults here: it reads scales[idx] from a null pointer.)"""
+    from diff_gaussian_rasterization import _C as ours, GaussianRasterizer
+    dev = torch.device("cuda")
+    cam, gs = gof_synth.make_scene(dict(P=20_000, width=320, height=240, seed=43), view=2)
+    P, W, H = 20_000, 320, 240
+    fa0 = _util.fwd_args(cam, gs, dev)
+    R0, c0, rad0, geo0, bin0, im0 = ours.rasterize_gaussians(*fa0)
+    v2g = ours.export_state(P, W, H, R0, geo0, bin0, im0, rad0)["view2gaussian"].contiguous().requires_grad_(True)
+    cov = _cov3d_from(gs["scales"], gs["rotations"], 1.0).to(dev)
+    rs = gof_synth.raster_settings(cam, gs["sh_degree"], dev)
+    means3D = gs["means3D"].to(dev).requires_grad_(True)
+    means2D = torch.zeros_like(means3D, requires_grad=True)
+    color, radii = GaussianRasterizer(rs)(means3D=means3D, means2D=means2D, opacities=gs["opacities"].to(dev), shs=gs["shs"].to(dev),
+                                          cov3D_precomp=cov, view2gaussian_precomp=v2g)
+    assert torch.equal(color[6], c0[6]) and torch.equal(color[7], c0[7]) and torch.equal(radii, rad0)
+    grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(8)).to(dev)
+    (color * grad).sum().backward()
+    g0 = ours.rasterize_gaussians_backward(*_util.bwd_args(fa0, rad0, geo0, R0, bin0, im0, grad))
+    assert _util.rel_err(v2g.grad, g0[8])[0] < 1e-5
+
+
+def test_error_in_debug_mode_dumps_snapshot(tmp_path, monkeypatch):
+    """debug=True: a failing native call writes the CPU snapshot of its inputs and re-raises
+    (diff_gaussian_rasterization/__init__.py:89-96 of the reference)."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    dev = torch.device("cuda")
+    cam, gs = gof_synth.make_scene(dict(P=500, width=64, height=48, seed=3), view=0)
+    rs = gof_synth.raster_settings(cam, 3, dev, debug=True)
+    monkeypatch.chdir(tmp_path)
+    bad_sh = gs["shs"][:, :4, :].contiguous().to(dev)            # degree 3 needs 16 coefficients: native validation fails
+    m3 = gs["means3D"].to(dev)
+    with pytest.raises(RuntimeError):
+        GaussianRasterizer(rs)(means3D=m3, means2D=torch.zeros_like(m3), opacities=gs["opacities"].to(dev), shs=bad_sh,
+                               scales=gs["scales"].to(dev), rotations=gs["rotations"].to(dev))
+    snap = torch.load(tmp_path / "snapshot_fw.dump")
+    assert isinstance(snap, tuple) and len(snap) == 22 and torch.equal(snap[1], gs["means3D"])   # the forward argument tuple
+    # without debug the same error is raised and nothing is written
+    (tmp_path / "snapshot_fw.dump").unlink()
+    rs2 = gof_synth.raster_settings(cam, 3, dev, debug=False)
+    with pytest.raises(RuntimeError):
+        GaussianRasterizer(rs2)(means3D=m3, means2D=torch.zeros_like(m3), opacities=gs["opacities"].to(dev), shs=bad_sh,
+                                scales=gs["scales"].to(dev), rotations=gs["rotations"].to(dev))
+    assert not (tmp_path / "snapshot_fw.dump").exists()

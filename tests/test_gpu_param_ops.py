@@ -1,4 +1,4 @@
-"""GPU (opt-in: GOF_STAGED=1 -- these wrappers have not had their first GPU run): gof_params.activate / adam_step against the
+"""GPU: gof_params.activate / adam_step / compute_3d_filter against the
 golden vectors generated from the reference's own Python (tests/golden/make_golden_params.py).  The arithmetic itself is
 checked on the CPU in test_param_ops_host.py."""
 import glob
@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GOF_STAGED") != "1", reason="staged: set GOF_STAGED=1")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIX = sorted(glob.glob(os.path.join(HERE, "golden", "params_*.npz")))
 
