@@ -132,6 +132,61 @@ int gof_read_back(void* dst, const void* src_dev, size_t bytes, cudaStream_t st)
   return GOF_OK;
 }
 
+// The instance count (num_rendered) sizes the binning buffer, so the host needs it in the middle of the forward
+// (rasterizer_impl.cu:334-340 does a blocking cudaMemcpy there, idling the GPU for the round trip).  Here the preprocess kernel
+// itself sums tiles_touched; the 4-byte copy runs on a side stream as soon as that kernel has finished, while the launching
+// stream carries on with the depth sort, and the host waits for the copy only: by the time it has sized the buffer and queued
+// the emit kernel the GPU is still busy sorting.
+bool gof_binning_legacy();
+namespace {
+struct SideCopy { cudaStream_t st = nullptr; cudaEvent_t after_kernel = nullptr, copied = nullptr; uint32_t* pin = nullptr; bool ok = false, tried = false; };
+SideCopy* side_copy_for_current_device() {
+  static thread_local SideCopy table[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideCopy& s = table[dev];
+  if (!s.tried) {
+    s.tried = true;
+    s.ok = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.after_kernel, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
+           cudaHostAlloc((void**)&s.pin, 64, cudaHostAllocDefault) == cudaSuccess;
+    if (!s.ok) (void)cudaGetLastError();
+  }
+  return s.ok ? &s : nullptr;
+}
+}  // namespace
+
+// Queues "copy *src_dev (u32) to the host once everything queued on `st` so far has finished" on the side stream.
+// Returns nullptr when side-stream resources are unavailable (the caller then reads back synchronously).
+static SideCopy* begin_async_read_u32(const void* src_dev, cudaStream_t st) {
+  SideCopy* sc = side_copy_for_current_device();
+  if (!sc) return nullptr;
+  if (cudaEventRecord(sc->after_kernel, st) != cudaSuccess || cudaStreamWaitEvent(sc->st, sc->after_kernel, 0) != cudaSuccess ||
+      cudaMemcpyAsync(sc->pin, src_dev, 4, cudaMemcpyDeviceToHost, sc->st) != cudaSuccess ||
+      cudaEventRecord(sc->copied, sc->st) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return sc;
+}
+static int finish_async_read_u32(SideCopy* sc, uint32_t* out) {
+  GOF_CUDA_OK(cudaEventSynchronize(sc->copied));
+  *out = *sc->pin;
+  return GOF_OK;
+}
+
+// Preprocess + depth sort + num_rendered, shared by forward and integrate.
+static int preprocess_sort_count(const gof_scene_t* s, const GofView& v, char* geom, const GofGeomLayout& GL, int* radii,
+                                 cudaStream_t st, uint32_t* R) {
+  int rc;
+  if ((rc = gof_launch_preprocess(s, v, geom, GL, radii, st)) != GOF_OK) return rc;
+  SideCopy* sc = (gof_binning_legacy() || s->debug) ? nullptr : begin_async_read_u32(geom + GL.total, st);
+  if ((rc = gof_depth_sort_and_offsets(s->P, geom, GL, s->debug != 0, st)) != GOF_OK) return rc;
+  if (sc) return finish_async_read_u32(sc, R);
+  return gof_read_back(R, geom + GL.total, sizeof(uint32_t), st);
+}
+
 static unsigned long long* g_stats_dev = nullptr;
 unsigned long long* gof_stats_buffer() {
   static int on = -1;
@@ -220,15 +275,11 @@ extern "C" int gof_rasterize_forward(const gof_scene_t* s, gof_alloc_fn geom_all
   if (!geom || !img) { gof_set_error("scratch allocator returned NULL"); return GOF_E_ALLOC; }
   tr.mark("alloc geom+img");
 
-  if ((rc = gof_launch_preprocess(s, v, geom, GL, radii, st)) != GOF_OK) return rc;
-  if ((rc = gof_depth_sort_and_offsets(s->P, geom, GL, s->debug != 0, st)) != GOF_OK) return rc;
-  tr.mark("launch pre+sort");
-
-  // rasterizer_impl.cu:334-340: the instance count sizes the binning buffer (one blocking D2H read)
+  // rasterizer_impl.cu:334-340: the instance count sizes the binning buffer (read while the depth sort runs)
   uint32_t R = 0;
-  if ((rc = gof_read_back(&R, geom + GL.total, sizeof(uint32_t), st)) != GOF_OK) return rc;
+  if ((rc = preprocess_sort_count(s, v, geom, GL, radii, st, &R)) != GOF_OK) return rc;
   *num_rendered = (int)R;
-  tr.mark("sync num_rendered");
+  tr.mark("pre+sort, num_rendered");
 
   const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height);
   char* bin = (char*)binning_alloc(binning_user, BL.bytes);
@@ -379,10 +430,8 @@ extern "C" int gof_integrate(const gof_scene_t* s, int PN, const float* points3D
   const GofImageLayout IL = gof_image_layout(s->width, s->height);
   char* img = (char*)image_alloc(image_user, IL.bytes);
   if (!geom || !img) { gof_set_error("scratch allocator returned NULL"); return GOF_E_ALLOC; }
-  if ((rc = gof_launch_preprocess(s, v, geom, GL, radii, st)) != GOF_OK) return rc;
-  if ((rc = gof_depth_sort_and_offsets(s->P, geom, GL, s->debug != 0, st)) != GOF_OK) return rc;
   uint32_t R = 0;
-  if ((rc = gof_read_back(&R, geom + GL.total, sizeof(uint32_t), st)) != GOF_OK) return rc;
+  if ((rc = preprocess_sort_count(s, v, geom, GL, radii, st, &R)) != GOF_OK) return rc;
   *num_rendered = (int)R;
   const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height, /*with_masks=*/false);
   char* bin = (char*)binning_alloc(binning_user, BL.bytes);

@@ -85,6 +85,45 @@ __device__ __forceinline__ float gof_lds32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
   return v;
 }
+// ---- bulk asynchronous copies (cp.async.bulk, the 1-D form of TMA) completing on an mbarrier -----------------------
+// A tile's slab is an INDIRECT gather of 64-byte records, which a tensor-map copy cannot express; one 1-D bulk copy per
+// record can: the copy engine moves the record global -> shared while the issuing thread carries on, and signals the
+// mbarrier of the staging buffer with the bytes it delivered (complete_tx).  `bar` / `dst` are shared-window addresses.
+__device__ __forceinline__ void gof_mbar_init(uint32_t bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void gof_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void gof_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gof_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gof_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GOF_MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GOF_MBAR_DONE_%=;\n"
+      "bra GOF_MBAR_WAIT_%=;\n"
+      "GOF_MBAR_DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void gof_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void gof_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only; completion through cp.async.wait_all + a CTA barrier
+__device__ __forceinline__ void gof_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gof_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void gof_sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void gof_sts32u(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 // 1/x, <= 1 ulp, no range guard (MUFU.RCP): for x known to be a normal number, or where inf/NaN are acceptable
 __device__ __forceinline__ float gof_rcp_approx(float x) {
   float r;
@@ -122,7 +161,8 @@ static_assert(sizeof(GofSplat) == 64, "GofSplat must be 64 bytes");
 struct __align__(16) GofSplatBwd {
   float mx, my;          // means2D
   float cx, cy, cz;      // 2D conic (used for the densification statistic only)
-  float pad[3];
+  uint32_t self;         // this Gaussian's index (the backward blend reads it from the staged row: accumulator row address)
+  float pad[2];
 };
 static_assert(sizeof(GofSplatBwd) == 32, "GofSplatBwd must be 32 bytes");
 
@@ -135,14 +175,23 @@ static inline size_t gof_align_up(size_t v, size_t a) { return (v + a - 1) / a *
 
 static inline int gof_sort_blocks(size_t n) { return (int)((n + GOF_SORT_CHUNK - 1) / GOF_SORT_CHUNK); }
 
+// Scratch of one radix sort of n pairs (binning.cu): global digit histograms of up to 4 passes [4][256], 64 ticket/flag words,
+// and per pass one decoupled-look-back status word per (chunk, digit).  (The pre-onesweep kernels, kept for A/B runs under
+// GOF_BINNING=legacy, need 256 * (blocks + 1) words of it.)
+#define GOF_SORT_HEAD_BYTES (4 * GOF_RADIX * 4 + 256)
+static inline size_t gof_sort_scratch_bytes(size_t n) {
+  return (size_t)GOF_SORT_HEAD_BYTES + (size_t)4 * (size_t)(gof_sort_blocks(n) + 1) * GOF_RADIX * 4;
+}
+
 struct GofGeomLayout {      // "geomBuffer": everything sized by P
   size_t splat, splat_bwd, rect, tiles, clamped, depth;
   size_t key_a, key_b, val_a, val_b;   // depth radix sort ping-pong
-  size_t offsets;                      // inclusive scan of tiles_touched in depth order
-  size_t hist;                         // radix block histograms [RADIX][blocks]
-  size_t scan_tmp;                     // scan block sums
+  size_t offsets;                      // inclusive scan of tiles_touched in depth order (legacy binning only)
+  size_t hist;                         // radix sort scratch (gof_sort_scratch_bytes)
+  size_t scan_tmp;                     // scan block sums / look-back status words
   size_t total;                        // u32 num_rendered (device copy)
   size_t grad_acc;                     // float[P][16]: backward accumulators of the blend kernel (dv2g[10], dcolor[3], dmean2D[3])
+  size_t reject_k;                     // float[P]: K' = (C + 2 thr)(1 - 4e-7), thr = -ln(255 opacity) - 2e-3: a pair with (B/2)^2 < A K' has alpha < 1/255
   size_t bytes;
 };
 
@@ -161,10 +210,11 @@ static inline GofGeomLayout gof_geom_layout(size_t P) {
   L.val_a = take(P * 4);
   L.val_b = take(P * 4);
   L.offsets = take(P * 4);
-  L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(P) + 1) * 4);
-  L.scan_tmp = take((P / 1024 + 2) * 4 + 4096);
+  L.hist = take(gof_sort_scratch_bytes(P));
+  L.scan_tmp = take((P / 256 + 8) * 4 + 4096);      // look-back status words of the fused scan+emit kernel (one per 256 Gaussians) + ticket
   L.total = take(256);
   L.grad_acc = take(P * 64);
+  L.reject_k = take(P * 4);
   L.bytes = o;
   return L;
 }
@@ -231,7 +281,7 @@ static inline GofBinLayout gof_bin_layout(size_t R, int W, int H, bool with_mask
   L.key_b = take(R * L.key_bytes);
   L.val_a = take(R * 4);
   L.val_b = take(R * 4);
-  L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(R) + 1) * 4);
+  L.hist = take(gof_sort_scratch_bytes(R));
   L.point_list = (L.passes % 2 == 0) ? L.val_a : L.val_b;
   L.sorted_keys = (L.passes % 2 == 0) ? L.key_a : L.key_b;
   L.vmask_stride = R + 32 * (size_t)tiles;
@@ -290,7 +340,7 @@ static inline GofPointBinLayout gof_point_bin_layout(size_t PN, int tiles, int s
   GofPointBinLayout L; size_t o = 0;
   auto take = [&](size_t b) { size_t r = o; o = gof_align_up(o + b, 256); return r; };
   L.key_a = take(PN * 4); L.key_b = take(PN * 4); L.val_a = take(PN * 4); L.val_b = take(PN * 4);
-  L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(PN) + 1) * 4);
+  L.hist = take(gof_sort_scratch_bytes(PN));
   L.pranges = take((size_t)(tiles + 1) * 8);
   L.nblk = tiles < sm_count * 3 ? tiles : sm_count * 3;
   if (L.nblk < 1) L.nblk = 1;

@@ -35,6 +35,8 @@ struct PreArgs {
   uint32_t* depth_key;  // depth bits for visible Gaussians, 0xFFFFFFFF otherwise (sorts last)
   uint32_t* order;      // identity permutation, the value array of the depth sort
   float* depth;         // view-space z of visible Gaussians (parity export)
+  uint32_t* total;      // sum of tiles_touched = num_rendered (zeroed by the launcher)
+  float* reject_k;      // see GofGeomLayout::reject_k
   int cull;             // 1: store the conservative alpha-support box, 0: store the whole plane
 };
 
@@ -139,7 +141,8 @@ __global__ void __launch_bounds__(256) k_preprocess(const PreArgs a) {
     rb.cx = F_MUL(cov.c, det_inv);
     rb.cy = F_MUL(det_inv, -cov.b);
     rb.cz = F_MUL(cov.a, det_inv);
-    rb.pad[0] = rb.pad[1] = rb.pad[2] = 0.f;
+    rb.self = (uint32_t)idx;
+    rb.pad[0] = rb.pad[1] = 0.f;
     rec.opacity = F_MUL(cov.coef, a.opacities[idx]);
     double lambda_min = 0.0;   // smallest eigenvalue of Sigma = min S^-2; unknown for a precomputed record
     // forward.cu:395-403 (the precomputed record is used with stride 10, rasterizer_impl.cu:379)
@@ -162,6 +165,19 @@ __global__ void __launch_bounds__(256) k_preprocess(const PreArgs a) {
     rec.box_lo = ((uint32_t)box.x0 & 0xffffu) | ((uint32_t)box.y0 << 16);
     rec.box_hi = ((uint32_t)box.x1 & 0xffffu) | ((uint32_t)box.y1 << 16);
     a.depth[idx] = tz;
+    // Constant of the blend kernel's conservative pair reject (render_fwd.cu): with thr = -ln(255 op) - 2e-3 (the margin
+    // covers expf and the float rounding of power) a pair is provably below alpha = 1/255 when
+    // -1/2 (C - (B/2)^2 / A) < thr  <=>  (B/2)^2 < A (C + 2 thr)  for A > 0.  K' carries a 4e-7 relative margin: the
+    // two float products of the test are each within 2^-24 and K' itself is rounded once (6e-8); K <= 0 (camera inside the iso-surface) or op <= 0 can never reject / always reject.
+    {
+      float kp;
+      if (!(rec.opacity > 0.f)) kp = __int_as_float(0x7f800000);            // +inf: every pair rejected (alpha <= 0)
+      else {
+        const double K = (double)rec.v2g[9] + 2.0 * (-(double)logf(255.0f * rec.opacity) - 2e-3);
+        kp = K > 0.0 ? (float)(K * (1.0 - 4e-7)) : __int_as_float(0xff800000);   // -inf: never rejected
+      }
+      a.reject_k[idx] = kp;
+    }
     float4* dst = reinterpret_cast<float4*>(a.splat + idx);
     const float4* srcr = reinterpret_cast<const float4*>(&rec);
     dst[0] = srcr[0]; dst[1] = srcr[1]; dst[2] = srcr[2]; dst[3] = srcr[3];
@@ -179,6 +195,13 @@ __global__ void __launch_bounds__(256) k_preprocess(const PreArgs a) {
   a.rect[idx] = rect_out;
   a.depth_key[idx] = key_out;
   a.order[idx] = (uint32_t)idx;
+  // num_rendered = sum of tiles_touched (the reference reads the last element of its inclusive scan, rasterizer_impl.cu:334-336).
+  // Summed here so that the host can read it while the depth sort runs; order-independent (integer adds).
+  {
+    const uint32_t active = __activemask();
+    const uint32_t wsum = __reduce_add_sync(active, tiles_out);
+    if ((int)(threadIdx.x & 31) == __ffs(active) - 1 && wsum) atomicAdd(a.total, wsum);
+  }
 }
 
 __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const float* __restrict__ vm,
@@ -527,6 +550,9 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
   a.depth_key = reinterpret_cast<uint32_t*>(geom + L.key_a);
   a.order = reinterpret_cast<uint32_t*>(geom + L.val_a);
   a.depth = reinterpret_cast<float*>(geom + L.depth);
+  a.total = reinterpret_cast<uint32_t*>(geom + L.total);
+  a.reject_k = reinterpret_cast<float*>(geom + L.reject_k);
+  GOF_CUDA_OK(cudaMemsetAsync(a.total, 0, 4, st));
   {
     static int cull = -1;   // GOF_CULL=0 disables the alpha-support boxes (A/B testing; results are identical)
     if (cull < 0) { const char* e = getenv("GOF_CULL"); cull = (e && e[0] == '0') ? 0 : 1; }

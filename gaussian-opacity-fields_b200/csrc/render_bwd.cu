@@ -8,6 +8,9 @@
 // backward visits exactly those (no box test, no reject arithmetic -- 44 % of the forward's visits blend nothing),
 // re-evaluating t, G and alpha with the forward's operation sequence (gof_math.cuh) so that they are bit-identical.
 // The traversal starts at the last Gaussian any pixel of the tile blended.
+// Staging of the per-tile slab (64-byte record + 32-byte backward record per list entry) as in render_fwd.cu: bulk copies
+// completing on an mbarrier (default), cp.async, or the round-1 load/store staging (GOF_STAGE=bulk|cpasync|regs), double
+// buffered in 2 x 24 KB of dynamic shared memory so that batch i-1 lands while batch i is walked.
 #include <stdlib.h>
 
 #include "gof_common.cuh"
@@ -64,14 +67,18 @@ __device__ __forceinline__ float warp_reduce16(const float (&a)[16], int lane) {
   return e;
 }
 
-template <bool STATS, int MINB>
+// STAGE: 0 = registers + st.shared (round 1), 1 = cp.async.bulk + mbarrier, 2 = cp.async (LDGSTS)
+template <bool STATS, int MINB, int STAGE>
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const BwdArgs a) {
+  constexpr bool BULK = STAGE == 1, CPA = STAGE == 2;
   unsigned long long st_visit = 0, st_eval = 0, st_pass = 0, st_contrib = 0, st_anyhit = 0;
-  // 28 KB: rows of 112 bytes per staged Gaussian = GofSplat (64 B) | GofSplatBwd (32 B) | (-, id, -, -); one row base
-  // register serves every load of a visit (see gof_smem_base)
-  __shared__ float4 s_rec[BATCH][7];
+  // rows of 96 bytes per staged Gaussian = GofSplat (64 B) | GofSplatBwd (32 B: means2D, 2D conic, own index); one row base
+  // register serves every load of a visit (see gof_smem_base).  One buffer (24 KB) for STAGE 0, two otherwise.
+  extern __shared__ __align__(128) float4 s_dyn[];
+  __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ uint32_t s_max;
-  const uint32_t s_base = gof_smem_base(&s_rec[0][0]);
+  const uint32_t s_base = gof_smem_base(s_dyn);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
 
   const int tile = blockIdx.x;
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
@@ -110,7 +117,14 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
   uint32_t warp_last = last_contributor;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, d));
-  if (threadIdx.x == 0) s_max = 0u;
+  if (threadIdx.x == 0) {
+    s_max = 0u;
+    if (BULK) {
+      gof_mbar_init(bar0, GOF_BLOCK_SIZE);
+      gof_mbar_init(bar0 + 8u, GOF_BLOCK_SIZE);
+      gof_mbar_init_fence();
+    }
+  }
   __syncthreads();
   if (lane == 0) atomicMax(&s_max, warp_last);
   __syncthreads();
@@ -129,22 +143,67 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
   //   v 10..12 -> dL_dcolor, v 13..15 -> dL_dmean2D
   const int vidx = lane >> 1;
 
-  // Batches are the forward's (entries [256*ib, 256*ib+256) of the tile list), taken from the deepest one the tile used
-  // down to 0; inside a batch the groups of 32 and the bits inside a group are walked from high to low: back to front.
+  // ---- staging: step s of the walk handles batch ib = rounds-1-s (entries [256*ib, 256*ib+256) of the tile list) out of
+  // buffer s & 1; its copies are issued one step earlier -------------------------------------------------------
+  uint32_t meta_id = 0;
+  auto load_meta = [&](int step) {
+    const int e = (rounds - 1 - step) * BATCH + (int)threadIdx.x;
+    if (step < rounds && e < used) meta_id = a.point_list[range.x + (uint32_t)e];
+  };
+  auto issue = [&](int step) {
+    const bool has = (rounds - 1 - step) * BATCH + (int)threadIdx.x < used;
+    const uint32_t row = s_base + (uint32_t)((step & 1) * BATCH + (int)threadIdx.x) * 96u;
+    if (BULK) {   // every thread arrives once per step on the buffer's mbarrier; threads with an entry add 96 bytes
+      const uint32_t bar = bar0 + 8u * (uint32_t)(step & 1);
+      if (has) {
+        gof_mbar_arrive_expect_tx(bar, 96u);
+        gof_bulk_g2s(row, a.splat + meta_id, 64u, bar);
+        gof_bulk_g2s(row + 64u, a.splat_bwd + meta_id, 32u, bar);
+      } else {
+        gof_mbar_arrive(bar);
+      }
+    } else if (has) {
+      const char* src = reinterpret_cast<const char*>(a.splat + meta_id);
+      const char* srcb = reinterpret_cast<const char*>(a.splat_bwd + meta_id);
+      gof_cp_async16(row, src); gof_cp_async16(row + 16u, src + 16);
+      gof_cp_async16(row + 32u, src + 32); gof_cp_async16(row + 48u, src + 48);
+      gof_cp_async16(row + 64u, srcb); gof_cp_async16(row + 80u, srcb + 16);
+    }
+  };
+  if (STAGE) {
+    load_meta(0);
+    if (rounds > 0) issue(0);
+    load_meta(1);
+  }
+
+  // Batches are the forward's, taken from the deepest one the tile used down to 0; inside a batch the groups of 32 and the
+  // bits inside a group are walked from high to low: back to front.
   for (int i = 0; i < rounds; ++i) {
     const int ib = rounds - 1 - i;
     const int base = ib * BATCH;
-    __syncthreads();
-    if (base + (int)threadIdx.x < used) {
-      const uint32_t g = a.point_list[range.x + (uint32_t)(base + (int)threadIdx.x)];
-      const float4* src = reinterpret_cast<const float4*>(a.splat + g);
-      const float4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
-      s_rec[threadIdx.x][0] = r0; s_rec[threadIdx.x][1] = r1; s_rec[threadIdx.x][2] = r2; s_rec[threadIdx.x][3] = r3;
-      const float4* srcb = reinterpret_cast<const float4*>(a.splat_bwd + g);
-      s_rec[threadIdx.x][4] = __ldg(srcb); s_rec[threadIdx.x][5] = __ldg(srcb + 1);
-      s_rec[threadIdx.x][6] = make_float4(0.f, __uint_as_float(g), 0.f, 0.f);
+    uint32_t buf_base = s_base;
+    if (STAGE) {
+      if (CPA) gof_cp_async_wait_all();   // this thread's copies of step i have landed; the barrier publishes everybody's
+      __syncthreads();                    // every warp has finished step i-1: its buffer may be refilled
+      buf_base = s_base + (uint32_t)(i & 1) * (uint32_t)(BATCH * 96);
+      if (i + 1 < rounds) {
+        issue(i + 1);                     // lands while this batch is walked
+        load_meta(i + 2);
+      }
+      if (BULK) gof_mbar_wait(bar0 + 8u * (uint32_t)(i & 1), (uint32_t)(i >> 1) & 1u);
+    } else {
+      __syncthreads();
+      if (base + (int)threadIdx.x < used) {
+        const uint32_t g = a.point_list[range.x + (uint32_t)(base + (int)threadIdx.x)];
+        const float4* src = reinterpret_cast<const float4*>(a.splat + g);
+        const float4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
+        float4* dst = s_dyn + (size_t)threadIdx.x * 6;
+        dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
+        const float4* srcb = reinterpret_cast<const float4*>(a.splat_bwd + g);
+        dst[4] = __ldg(srcb); dst[5] = __ldg(srcb + 1);
+      }
+      __syncthreads();
     }
-    __syncthreads();
 
     // the loop is NOT unrolled (one copy of the body, see render_fwd.cu)
 #pragma unroll 1
@@ -164,7 +223,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         bool contrib = ((mybits >> b) & 1u) != 0u;   // implies inside && contributor < last_contributor
         if (STATS) { st_visit += (lane == 0); st_eval += contrib; st_pass += contrib; }
 
-        const uint32_t row = s_base + (uint32_t)j * 112u;
+        const uint32_t row = buf_base + (uint32_t)j * 96u;
         const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
         const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
         GofPair p;
@@ -264,7 +323,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
         const float sum = warp_reduce16(g, lane);
         // one red per even lane into the Gaussian's 64-byte accumulator row: 16 global float atomics per (warp, Gaussian)
         // instead of 17 per (pixel, Gaussian); dL_dopacity = -2/opacity * sum(dL_dC) is formed by k_preprocess_backward
-        const uint32_t gid = __float_as_uint(gof_lds32<100>(row));
+        const uint32_t gid = __float_as_uint(gof_lds32<84>(row));   // GofSplatBwd::self
         if (!(lane & 1) && sum != 0.f) atomicAdd(a.grad_acc + ((size_t)gid * 16 + vidx), sum);
       }
     }
@@ -297,12 +356,32 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geo
   a.grad_acc = reinterpret_cast<float*>(geom + GL.grad_acc);
   GOF_CUDA_OK(cudaMemsetAsync(a.grad_acc, 0, (size_t)s->P * 64, st));
   a.stats = gof_stats_buffer();
-  static int occ = -1;   // GOF_BWD_OCC=2|3|4 (tuning knob)
+  static int occ = -1, stage = -1;   // GOF_BWD_OCC=2|3|4 (tuning knob); GOF_STAGE: staging variant (see render_fwd.cu)
   if (occ < 0) { const char* e = getenv("GOF_BWD_OCC"); occ = e ? atoi(e) : 4; }
-  if (a.stats) GOF_LAUNCH("render_bwd", st, k_render_backward<true, 3><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
-  else if (occ >= 4) GOF_LAUNCH("render_bwd", st, k_render_backward<false, 4><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
-  else if (occ <= 2) GOF_LAUNCH("render_bwd", st, k_render_backward<false, 2><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
-  else GOF_LAUNCH("render_bwd", st, k_render_backward<false, 3><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  if (stage < 0) { const char* e = getenv("GOF_STAGE"); stage = !e ? 1 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1)); }
+  const size_t smem = (size_t)(stage ? 2 : 1) * BATCH * 96;
+#define GOF_BWD_LAUNCH(STATS, MINB, STG)                                                                                      \
+  do {                                                                                                                        \
+    static bool attr_set = false;                                                                                             \
+    if (!attr_set) {                                                                                                          \
+      GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BATCH * 96)); \
+      GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG>, cudaFuncAttributePreferredSharedMemoryCarveout,                \
+                                       (int)cudaSharedmemCarveoutMaxShared));                                                             \
+      attr_set = true;                                                                                                        \
+    }                                                                                                                         \
+    GOF_LAUNCH("render_bwd", st, k_render_backward<STATS, MINB, STG><<<v.tiles, GOF_BLOCK_SIZE, smem, st>>>(a));             \
+  } while (0)
+#define GOF_BWD_STAGES(STATS, MINB)                                                                   \
+  do {                                                                                                \
+    if (stage == 1) GOF_BWD_LAUNCH(STATS, MINB, 1); else if (stage == 2) GOF_BWD_LAUNCH(STATS, MINB, 2); \
+    else GOF_BWD_LAUNCH(STATS, MINB, 0);                                                              \
+  } while (0)
+  if (a.stats) GOF_BWD_STAGES(true, 3);
+  else if (occ >= 4) GOF_BWD_STAGES(false, 4);
+  else if (occ <= 2) GOF_BWD_STAGES(false, 2);
+  else GOF_BWD_STAGES(false, 3);
+#undef GOF_BWD_STAGES
+#undef GOF_BWD_LAUNCH
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }

@@ -2,8 +2,14 @@
 //
 // One 256-thread CTA per 16x16 tile.  Differences from the reference that do not change results:
 //  * a warp covers an 8x4 pixel block (not a 16x2 strip) so the 32 rays of a warp are spatially compact;
-//  * each (tile,Gaussian) instance is gathered as ONE 64-byte record (two sectors) and the gather for batch
-//    i+1 is issued before batch i is blended (register double buffering);
+//  * each (tile,Gaussian) instance is gathered as ONE 64-byte record (two sectors).  The per-tile slab is staged by the
+//    copy engine: every thread issues one 64-byte cp.async.bulk (global -> shared, completing on the mbarrier of the
+//    staging buffer) for its entry of batch i+1 while batch i is blended out of the other buffer (forward.cu:472-491 is a
+//    load/store/__syncthreads loop).  No registers hold records in flight (the register double buffer of round 1 cost
+//    16 registers and spills at 4 CTAs/SM) and a batch needs ONE CTA barrier instead of two.  ptxas issues a per-thread
+//    bulk copy from the uniform datapath, one elected lane at a time (UBLKCP inside an ELECT loop, ~9 issue slots per
+//    record); the third variant uses four 16-byte cp.async (LDGSTS) per record instead -- same double buffer, completion by
+//    cp.async.wait_all + the batch barrier.  GOF_STAGE=bulk|cpasync|regs selects the variant (regs = round 1) for A/B timing;
 //  * every record carries a conservative pixel box of the region where its alpha can reach 1/255
 //    (gof_cull_bbox); each warp ballots the 256 staged boxes against its own 8x4 pixel block and only visits
 //    the Gaussians that can touch it;
@@ -27,6 +33,7 @@ struct FwdArgs {
   const uint2* ranges;
   const uint32_t* point_list;
   const GofSplat* splat;
+  const float* reject_k;   // GofGeomLayout::reject_k
   const float* bg;
   float* accum;        // [4][tiles*256] tile-major
   uint32_t* ncontrib;  // [2][tiles*256]
@@ -44,12 +51,16 @@ __device__ __forceinline__ bool box_hits(uint32_t lo, uint32_t hi, int wx0, int 
   return x0 <= wx1 && x1 >= wx0 && y0 <= wy1 && y1 >= wy0;
 }
 
-template <int MINB>
+// STAGE: 0 = registers + st.shared (round 1), 1 = cp.async.bulk + mbarrier, 2 = cp.async (LDGSTS)
+template <int MINB, int STAGE>
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const FwdArgs a) {
-  // 20 KB: rows of 80 bytes = the 64-byte record of a staged Gaussian + (thr, -, -, -), thr = -ln(255*opacity): the
-  // largest power that can still be rejected.  One row base serves every load of a visit.
-  __shared__ float4 s_rec[BATCH][5];
-  const uint32_t s_base = gof_smem_base(&s_rec[0][0]);
+  // Rows of 80 bytes = the 64-byte record of a staged Gaussian + (K', -, -, -), K' = the reject constant (see
+  // GofGeomLayout::reject_k).  One row base serves every load of a visit.  BULK: two buffers (40 KB), filled by bulk copies.
+  constexpr bool BULK = STAGE == 1, CPA = STAGE == 2;
+  __shared__ __align__(128) float4 s_rec[STAGE ? 2 : 1][BATCH][5];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  const uint32_t s_base = gof_smem_base(&s_rec[0][0][0]);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
 
   const int tile = blockIdx.x;
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
@@ -73,39 +84,88 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
   float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, Dm = 0.f, Aacc = 0.f;
   float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
 
-  // prefetch batch 0
-  float4 nx0, nx1, nx2, nx3;
+  // ---- staging ------------------------------------------------------------------------------------------------
+  // BULK: meta_id / meta_k hold this thread's list entry of the batch that is issued NEXT.
+  uint32_t meta_id = 0;
+  float meta_k = 0.f;
+  float4 nx0, nx1, nx2, nx3;   // !BULK: the record in flight
   nx0 = nx1 = nx2 = nx3 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if ((int)threadIdx.x < total) {
+  auto load_meta = [&](int batch) {
+    const int e = batch * BATCH + (int)threadIdx.x;
+    if (e < total) {
+      meta_id = a.point_list[range.x + e];
+      meta_k = __ldg(a.reject_k + meta_id);
+    }
+  };
+  auto issue = [&](int batch) {
+    const bool has = batch * BATCH + (int)threadIdx.x < total;
+    const uint32_t row = s_base + (uint32_t)((batch & 1) * BATCH + (int)threadIdx.x) * 80u;
+    if (BULK) {   // every thread arrives once per batch on the buffer's mbarrier; threads with an entry add 64 bytes
+      const uint32_t bar = bar0 + 8u * (uint32_t)(batch & 1);
+      if (has) {
+        gof_mbar_arrive_expect_tx(bar, 64u);
+        gof_bulk_g2s(row, a.splat + meta_id, 64u, bar);
+      } else {
+        gof_mbar_arrive(bar);
+      }
+    } else if (has) {
+      const char* src = reinterpret_cast<const char*>(a.splat + meta_id);
+      gof_cp_async16(row, src); gof_cp_async16(row + 16u, src + 16);
+      gof_cp_async16(row + 32u, src + 32); gof_cp_async16(row + 48u, src + 48);
+    }
+    if (has) gof_sts32(row + 64u, meta_k);
+  };
+  if (STAGE) {
+    if (BULK) {
+      if (threadIdx.x == 0) {
+        gof_mbar_init(bar0, GOF_BLOCK_SIZE);
+        gof_mbar_init(bar0 + 8u, GOF_BLOCK_SIZE);
+        gof_mbar_init_fence();
+      }
+      __syncthreads();
+    }
+    load_meta(0);
+    issue(0);
+    load_meta(1);
+  } else if ((int)threadIdx.x < total) {
     const uint32_t g = a.point_list[range.x + threadIdx.x];
     const float4* src = reinterpret_cast<const float4*>(a.splat + g);
     nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2); nx3 = __ldg(src + 3);
+    meta_k = __ldg(a.reject_k + g);
   }
 
   int toDo = total;
-  for (int i = 0; i < rounds; ++i, toDo -= BATCH) {
-    // forward.cu:475-477: stop when every pixel of the tile is saturated
+  int i = 0;
+  for (; i < rounds; ++i, toDo -= BATCH) {
+    // forward.cu:475-477: stop when every pixel of the tile is saturated.  The barrier also says: every warp has finished
+    // with the buffer of batch i-1, and the K' values of batch i (plain stores) are visible.
+    if (CPA) gof_cp_async_wait_all();   // this thread's copies of batch i have landed; the barrier publishes everybody's
     if (__syncthreads_and(done)) break;
-    s_rec[threadIdx.x][0] = nx0; s_rec[threadIdx.x][1] = nx1;
-    s_rec[threadIdx.x][2] = nx2; s_rec[threadIdx.x][3] = nx3;
-    {
-      const float op = nx2.z;   // (v2g[8], v2g[9], opacity, rgb0)
-      // alpha = op*exp(power) < 1/255  <=>  power < -ln(255*op);   op <= 0 can never contribute
-      s_rec[threadIdx.x][4].x = (op > 0.f) ? (-logf(255.0f * op) - 2e-3f) : __int_as_float(0x7f800000);
-    }
-    __syncthreads();
-    // issue the gather for the next batch; it completes while this batch is blended
-    {
+    uint32_t buf_base = s_base;
+    if (STAGE) {
+      buf_base = s_base + (uint32_t)(i & 1) * (uint32_t)(BATCH * 80);
+      if (i + 1 < rounds) {
+        issue(i + 1);        // lands while this batch is blended
+        load_meta(i + 2);
+      }
+    } else {
+      s_rec[0][threadIdx.x][0] = nx0; s_rec[0][threadIdx.x][1] = nx1;
+      s_rec[0][threadIdx.x][2] = nx2; s_rec[0][threadIdx.x][3] = nx3;
+      s_rec[0][threadIdx.x][4].x = meta_k;
+      __syncthreads();
+      // issue the gather for the next batch; it completes while this batch is blended
       const int nxt = (i + 1) * BATCH + (int)threadIdx.x;
       if (nxt < total) {
         const uint32_t g = a.point_list[range.x + nxt];
         const float4* src = reinterpret_cast<const float4*>(a.splat + g);
         nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2); nx3 = __ldg(src + 3);
+        meta_k = __ldg(a.reject_k + g);
       }
     }
 
     const int nb = toDo < BATCH ? toDo : BATCH;
-    if (__all_sync(0xffffffffu, done)) continue;   // this warp's 32 pixels are saturated (it still helps staging)
+    if (__all_sync(0xffffffffu, done)) continue;   // this warp's 32 pixels are saturated (it still takes part in the staging)
+    if (BULK) gof_mbar_wait(bar0 + 8u * (uint32_t)(i & 1), (uint32_t)(i >> 1) & 1u);   // batch i has landed
 
     // Sub-batches of 32: ballot which of these 32 staged Gaussians can reach this warp's 8x4 pixels at all, then
     // visit only those.  (The loop is deliberately NOT unrolled: the body is ~10 KB of SASS and eight copies
@@ -114,7 +174,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
     for (int k = 0; k < BATCH / 32; ++k) {
       if (k * 32 >= nb) break;
       const int idx = k * 32 + lane;
-      const float4 qb = s_rec[idx][3];
+      const float4 qb = gof_lds128<48>(buf_base + (uint32_t)idx * 80u);
       uint32_t m = __ballot_sync(0xffffffffu, idx < nb && box_hits(__float_as_uint(qb.z), __float_as_uint(qb.w), wx0, wy0, wx0 + 7, wy0 + 3));
       uint32_t mybits = 0u;   // bit b: this pixel blended entry k*32+b of the batch
       while (m) {
@@ -124,19 +184,15 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
         bool blended = false;
         if (!done) {
           const uint32_t contributor = (uint32_t)(i * BATCH + j + 1);   // 1-based position in the tile list
-          const uint32_t row = s_base + (uint32_t)j * 80u;
+          const uint32_t row = buf_base + (uint32_t)j * 80u;
           const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
           const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
           const GofPair p = gof_pair_geom(v, rx, ry);
 
-          // ---- conservative reject (single precision, error-bounded) ----
+          // ---- conservative reject (single precision, division-free): alpha < 1/255 is certain when
+          // (B/2)^2 < A * K' with A > 0 (derivation and margins at GofGeomLayout::reject_k / k_preprocess) ----
           const float bh = 0.5f * p.BB;
-          // ~ BB^2/(4AA): bh*bh (1/2 ulp), MUFU.RCP (1 ulp, AA denormal -> inf -> not rejected), product (1/2 ulp):
-          // relative error <= 2.4e-7 < 3.5e-7
-          const float qf = bh * bh * gof_rcp_approx(p.AA);
-          const float pw = -0.5f * (v[9] - qf);                  // approximate power
-          const float bound = fmaf(fabsf(qf), 3.5e-7f, pw);      // pw + |error|
-          if (!(bound < gof_lds32<64>(row) && fabsf(p.AA) < 1e30f)) {
+          if (!(F_MUL(bh, bh) < F_MUL(p.AA, gof_lds32<64>(row)) && p.AA > 0.f)) {
             // ---- exact path: forward.cu:516-541 ----
             float t, power;
             gof_pair_t_power(p, v[9], &t, &power);
@@ -183,6 +239,10 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_forward(const F
     }
   }
 
+  // a CTA must not exit with copies in flight towards its shared memory: after an early break batch i may still be landing
+  if (BULK && i < rounds) gof_mbar_wait(bar0 + 8u * (uint32_t)(i & 1), (uint32_t)(i >> 1) & 1u);
+  if (CPA) gof_cp_async_wait_all();
+
   // forward.cu:584-611
   const size_t slot = (size_t)tile * 256 + threadIdx.x;
   a.accum[slot] = T;
@@ -218,6 +278,7 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
   a.ranges = reinterpret_cast<const uint2*>(img + IL.ranges);
   a.point_list = reinterpret_cast<const uint32_t*>(bin + BL.point_list);
   a.splat = reinterpret_cast<const GofSplat*>(geom + GL.splat);
+  a.reject_k = reinterpret_cast<const float*>(geom + GL.reject_k);
   a.bg = s->background;
   a.accum = reinterpret_cast<float*>(img + IL.accum);
   a.ncontrib = reinterpret_cast<uint32_t*>(img + IL.ncontrib);
@@ -225,10 +286,22 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
   a.plane = (size_t)v.tiles * 256;
   a.vmask = reinterpret_cast<uint32_t*>(bin + BL.vmask);
   a.vstride = BL.vmask_stride;
-  static int occ = -1;   // GOF_FWD_OCC=3|4: resident CTAs per SM the kernel is compiled for (tuning knob)
+  static int occ = -1, stage = -1;   // GOF_FWD_OCC=3|4: resident CTAs per SM the kernel is compiled for; GOF_STAGE: staging variant
   if (occ < 0) { const char* e = getenv("GOF_FWD_OCC"); occ = e ? atoi(e) : 4; }
-  if (occ >= 4) GOF_LAUNCH("render_fwd", st, k_render_forward<4><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
-  else GOF_LAUNCH("render_fwd", st, k_render_forward<3><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));
+  if (stage < 0) { const char* e = getenv("GOF_STAGE"); stage = !e ? 1 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1)); }
+#define GOF_FWD_LAUNCH(MINB, STG)                                                                                              \
+  do {                                                                                                                        \
+    static bool attr_set = false;   /* 4 CTAs x 40 KB of staging buffers per SM: ask for the large shared-memory carveout */   \
+    if (!attr_set) {                                                                                                          \
+      GOF_CUDA_OK(cudaFuncSetAttribute(k_render_forward<MINB, STG>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
+                                       (int)cudaSharedmemCarveoutMaxShared));                                                \
+      attr_set = true;                                                                                                        \
+    }                                                                                                                         \
+    GOF_LAUNCH("render_fwd", st, k_render_forward<MINB, STG><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));                        \
+  } while (0)
+  if (occ >= 4) { if (stage == 1) GOF_FWD_LAUNCH(4, 1); else if (stage == 2) GOF_FWD_LAUNCH(4, 2); else GOF_FWD_LAUNCH(4, 0); }
+  else { if (stage == 1) GOF_FWD_LAUNCH(3, 1); else if (stage == 2) GOF_FWD_LAUNCH(3, 2); else GOF_FWD_LAUNCH(3, 0); }
+#undef GOF_FWD_LAUNCH
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;
 }

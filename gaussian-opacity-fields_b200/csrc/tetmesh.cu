@@ -37,7 +37,7 @@ static TetLayout tet_layout(size_t T) {
   L.scan_tmp = take((I / 2048 + 4) * 4 + 4096);
   L.lo_a = take(I * 4); L.lo_b = take(I * 4); L.hi = take(I * 4);
   L.val_a = take(I * 4); L.val_b = take(I * 4);
-  L.hist = take((size_t)GOF_RADIX * (gof_sort_blocks(I) + 1) * 4);
+  L.hist = take(gof_sort_scratch_bytes(I));
   L.head = take(I * 4); L.uid_sorted = take(I * 4); L.inst_uid = take(I * 4);
   L.bytes = o;
   return L;
@@ -203,6 +203,7 @@ int gof_marching_tets_count(int num_verts, const float* sdf, int64_t num_tets, c
   uint32_t *cross_off = (uint32_t*)(S + L.cross_off), *f1_off = (uint32_t*)(S + L.f1_off), *f2_off = (uint32_t*)(S + L.f2_off);
   uint32_t* tmp = (uint32_t*)(S + L.scan_tmp);
   Header* hd = (Header*)(S + L.header);
+  GOF_CUDA_OK(cudaMemsetAsync(hd, 0, sizeof(Header), st));   // n_edges is read back (with the rest) before it is written
   const unsigned grid = (unsigned)((T + 255) / 256);
   GOF_LAUNCH("tet_classify", st, k_tet_classify<<<grid, 256, 0, st>>>(num_tets, sdf, tets, code, cross, f1, f2));
   GOF_LAUNCH_CHECK(false, st);

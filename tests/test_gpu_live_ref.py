@@ -154,7 +154,11 @@ def test_cov3d_precomp_against_live_reference(ref, with_v2g):
     if with_v2g:
         R0, c0, rad0, geo0, bin0, im0 = ours.rasterize_gaussians(*_util.fwd_args(cam, gs, dev, kernel_size=0.1))
         v2g = ours.export_state(P, W, H, R0, geo0, bin0, im0, rad0)["view2gaussian"]
-        fa[8] = (v2g * 1.0).contiguous()
+        # the export holds records of the Gaussians visible with the ORIGINAL covariance; the inflated one makes a few more
+        # visible -- give those a well-formed record (an isotropic sigma = 0.01 Gaussian 5 units in front of the camera) rather
+        # than zeros (A = B = 0 -> NaN depth in both implementations)
+        filler = torch.tensor([1e4, 0.0, 0.0, 1e4, 0.0, 1e4, 0.0, 0.0, -5e4, 25e4], device=dev)
+        fa[8] = torch.where((rad0 > 0)[:, None], v2g, filler[None, :]).contiguous()
         del geo0, bin0, im0
     fa = tuple(fa)
     Ro, co, rado, geo, bino, imo = ours.rasterize_gaussians(*fa)

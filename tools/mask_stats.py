@@ -28,7 +28,7 @@ def bin_layout(R, tiles):
     nb = (R + 4095) // 4096
     o = 0
     offs = {}
-    for name, nbytes in (("key_a", R * 2), ("key_b", R * 2), ("val_a", R * 4), ("val_b", R * 4), ("hist", 256 * (nb + 1) * 4)):
+    for name, nbytes in (("key_a", R * 2), ("key_b", R * 2), ("val_a", R * 4), ("val_b", R * 4), ("hist", 4352 + 4 * (nb + 1) * 1024)):
         offs[name] = o
         o = align(o + nbytes)
     offs["vmask"] = o
