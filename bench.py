@@ -534,6 +534,294 @@ def run_reference(args, rank, world, dev):
     }
 
 
+# ==============================================================================================================
+# Config C5: opacity-field mesh extraction (BASELINE.json configs[4]): 3 M Gaussians, 50 M query points, 64 views
+# ==============================================================================================================
+EXTRACT_METRIC = "opacity-field query points/sec (integrate, one 1080p view per step) over 3M Gaussians"
+EXTRACT_WORKLOAD_FMT = ("{cfg}: {P} Gaussians, {PN} query points (9 per Gaussian like get_tetra_points + samples in the 3-sigma boxes), "
+                        "{W}x{H}, {nv}-view ring, 1 view/step/GPU")
+
+
+class ExtractWorkload:
+    def __init__(self, args, dev, rank, world):
+        cfg = dict(gof_synth.CONFIGS[args.config])
+        self.P = cfg["P"]
+        self.PN = int(args.points or cfg.get("points", 10 * cfg["P"]))
+        self.n_views = int(args.views or cfg.get("n_views", 64))
+        self.W, self.H, self.dev, self.rank, self.world, self.cfg = cfg["width"], cfg["height"], dev, rank, world, cfg
+        cam0 = gof_synth.make_camera(self.W, self.H, view=0)
+        gs = gof_synth.make_gaussians(self.P, cfg["seed"], cam0.focal_x)
+        self.gs = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in gs.items()}
+        self.cams = [gof_synth.make_camera(self.W, self.H, view=v, n_views=self.n_views) for v in range(self.n_views)]
+        self.points, self.pscale = gof_synth.make_tetra_points(self.gs, self.PN, cfg["seed"] + 100, dev)
+        self.bg = torch.zeros(3, device=dev)
+        self.subpix = torch.zeros((self.H, self.W, 2), dtype=torch.float32, device=dev)
+        self.cam_host = [torch.cat([c.world_view_transform.flatten(), c.full_proj_transform.flatten(), c.camera_center]).pin_memory()
+                         for c in self.cams]
+
+    def view(self, step):
+        return (step * self.world + self.rank) % self.n_views
+
+    def settings(self, cls, v, cam_buf=None):
+        c = self.cams[v]
+        vm = c.world_view_transform.to(self.dev) if cam_buf is None else cam_buf[:16].view(4, 4)
+        pm = c.full_proj_transform.to(self.dev) if cam_buf is None else cam_buf[16:32].view(4, 4)
+        cp = c.camera_center.to(self.dev) if cam_buf is None else cam_buf[32:35]
+        return cls(image_height=self.H, image_width=self.W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, kernel_size=0.0,
+                   subpixel_offset=self.subpix, bg=self.bg, scale_modifier=1.0, viewmatrix=vm, projmatrix=pm, sh_degree=3, campos=cp,
+                   prefiltered=False, debug=False)
+
+
+def extract_e2e(args, wl, world, dev, rasterizer_cls, settings_cls):
+    """End to end through a package's public API: GaussianRasterizer(settings).integrate(points3D=...) for this step's view,
+    camera copied from pinned host memory every step, the smallest integrated alpha read back (4 bytes).  The query points
+    are the step-invariant operand of an extraction pass (extract_mesh.py evaluates the same points for all views) and
+    stay resident.  Same function for both arms."""
+    g = wl.gs
+    cam_buf = torch.empty(35, device=dev)
+    res_pin = torch.zeros(1).pin_memory()
+    m2d = torch.zeros_like(g["means3D"])
+
+    def step(i):
+        v = wl.view(i)
+        cam_buf.copy_(wl.cam_host[v], non_blocking=True)
+        rs = wl.settings(settings_cls, v, cam_buf)
+        with torch.no_grad():
+            _img, alpha, _col, _rad = rasterizer_cls(rs).integrate(points3D=wl.points, means3D=g["means3D"], means2D=m2d,
+                                                                   opacities=g["opacities"], shs=g["shs"], scales=g["scales"],
+                                                                   rotations=g["rotations"])
+        res_pin.copy_(alpha.min().reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+        return float(res_pin[0])
+
+    for i in range(max(2, args.warmup // 2)):
+        step(i)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    vals = [step(args.warmup + i) for i in range(args.steps)]
+    barrier_sync(world)
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    assert all(math.isfinite(x) for x in vals)
+    return ms
+
+
+def run_extract_ours(args, rank, world, dev):
+    from diff_gaussian_rasterization import _C, GaussianRasterizer, GaussianRasterizationSettings
+    import gof_extract
+    wl = ExtractWorkload(args, dev, rank, world)
+    g = wl.gs
+    ci = gof_extract.CachedIntegrator(g["means3D"], g["opacities"], g["scales"], g["rotations"], g["shs"], 3,
+                                      lambda v: wl.settings(GaussianRasterizationSettings, v))
+    # Gaussian side of this rank's views, once (SURVEY 8(f) rank 3): timed separately
+    my_views = sorted({wl.view(s) for s in range(args.warmup + args.steps)})
+    torch.cuda.synchronize()
+    p0 = time.perf_counter()
+    for v in my_views:
+        ci.prepare(v)
+    torch.cuda.synchronize()
+    prepare_ms = (time.perf_counter() - p0) * 1e3 / max(len(my_views), 1)
+
+    def step_device(s):
+        return ci(wl.points, wl.view(s))
+
+    for s in range(args.warmup):
+        step_device(s)
+    barrier_sync(world)
+    launches0 = _C.launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    e0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record()
+    barrier_sync(world)
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = _C.launch_count() - launches0
+    prof_steps = min(args.steps, 3)
+    _C.profile_reset(); _C.profile_enable(True)
+    for s in range(prof_steps):
+        step_device(args.warmup + s)
+    torch.cuda.synchronize(); _C.profile_enable(False)
+    prof = _C.profile_report()
+
+    # workload statistics of rank 0's first timed view
+    sv = wl.view(args.warmup)
+    _vw, rs_sv, cache_sv = ci.prepare(sv)
+    img_sv, _a, _c = _C.integrate_points_cached(cache_sv, wl.bg, wl.points, rs_sv.viewmatrix, rs_sv.tanfovx, rs_sv.tanfovy)
+    PNv = int(img_sv[8].sum().item())
+    Rg, Vg = int(cache_sv.num_rendered), int((cache_sv.radii > 0).sum())
+    N = wl.W * wl.H
+    del img_sv
+
+    e2e_ms = extract_e2e(args, wl, world, dev, GaussianRasterizer, GaussianRasterizationSettings)
+
+    # the whole extraction once (untimed against the headline): evaluate_alpha on all vertices, marching tetrahedra, 8 bisection steps
+    pipeline = None
+    if not args.no_pipeline:
+        T = int(wl.PN * wl.cfg.get("tets_per_point", 6.5)) if not args.tets else int(args.tets)
+        tets = gof_synth.make_local_tets(wl.PN, T, wl.cfg["seed"] + 200, dev)
+        views = list(range(wl.n_views))
+        tm = {}
+        torch.cuda.synchronize(); barrier_sync(world)
+        t0 = time.perf_counter()
+        out = gof_extract.extract_level_set(wl.points, wl.pscale, tets, views, ci, n_binary_steps=8,
+                                            group=None if world == 1 else dist.group.WORLD, timings=tm)
+        torch.cuda.synchronize(); barrier_sync(world)
+        total_s = max_over_ranks(time.perf_counter() - t0, world, dev)
+        pipeline = {"tets": T, "faces": int(out["faces"].shape[0]), "mesh_vertices": int(out["vertices"].shape[0]), "views": wl.n_views,
+                    "total_s": total_s, **{k: round(v, 4) for k, v in tm.items()},
+                    "tets_per_s": T / max(tm.get("marching_tetrahedra_s", 1e-9), 1e-9),
+                    "cached_view_bytes": int(ci.cached_bytes),
+                    "what": "gof_extract.extract_level_set: evaluate_alpha on the tetrahedra vertices (view-sharded, one all_reduce(MIN)), "
+                            "marching tetrahedra (tet-chunk sharded), 8 bisection steps, Gaussian side of every view cached"}
+        del tets, out
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # SURVEY 8(d), extraction: the query kernel gathers 72 B per tile instance (records of the tile lists), reads 16 B and writes
+    # 16 B per projected point, writes the 9-channel image; the point side in front of it reads 12 B/point and writes 24 B/projected point
+    k_bytes = 72 * Rg + 32 * PNv + 36 * N
+    view_bytes = k_bytes + 12 * wl.PN + 24 * PNv
+    cnt, k_ms = prof.get("integrate", (1, 0.0))
+    achieved = (k_bytes / (k_ms / max(cnt, 1) * 1e-3) / 1e9) if k_ms > 0 else None
+    line = {
+        "metric": EXTRACT_METRIC, "value": world * args.steps * wl.PN / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": EXTRACT_WORKLOAD_FMT.format(cfg=args.config, P=wl.P, PN=wl.PN, W=wl.W, H=wl.H, nv=wl.n_views),
+                   "stats_view": sv, "visible": Vg, "num_rendered": Rg, "points_projected": PNv,
+                   "parallelism": f"view-parallel dp{world}" if world > 1 else "single GPU",
+                   "gaussian_side": f"prepared once per view and cached ({prepare_ms:.2f} ms/view, outside the timed steps; the e2e "
+                                    f"number below repeats it every step like the reference)",
+                   "l2": "no explicit flush: a step streams the 50 M points (> 1 GB, > 126 MB L2) and every step is a new view"},
+        "e2e": {"value": world * args.steps * wl.PN / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": 35 * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                "api": "GaussianRasterizer(settings).integrate(points3D=...) incl. the Gaussian side; camera from pinned host memory every "
+                       "step, min(alpha_integrated) read back; query points resident (one extraction pass evaluates the same points for all views)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "integrate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "algorithmic_bytes_per_launch": k_bytes, "launch_ms": k_ms / max(cnt, 1), "step_algorithmic_bytes": view_bytes,
+                     "step_frac": view_bytes / ((ms / args.steps) * 1e-3) / 1e9 / peak},
+        "kernels_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+    if pipeline is not None:
+        line["extraction"] = pipeline
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_extract(wl)
+    return line
+
+
+def cpu_baseline_extract(wl):
+    """The reference's query algorithm on the host cores (oracle/ port, OpenMP) for one view: Gaussian side of the full view,
+    point side on a bounded sample -- the top 64 pixel rows' tiles and the query points that project into them."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ctypes
+    import numpy as np
+    import gof_oracle
+    gs_cpu = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in wl.gs.items()}
+    cam = wl.cams[1]
+    sc = gof_oracle.scene_from_synth(cam, gs_cpu)
+    t0 = time.perf_counter()
+    g = gof_oracle.preprocess(sc)
+    R, plist, ranges = gof_oracle.bin_tiles(sc.W, sc.H, g["radii"], g["means2D"], g["depths"], g["tiles_touched"])
+    t1 = time.perf_counter()
+    rows = 64
+    gx = (sc.W + 15) // 16
+    ranges_s = np.ascontiguousarray(ranges, np.uint32).copy()
+    ranges_s[(rows // 16) * gx:] = 0
+    # points that project into the kept rows (same projection as forward.cu:756-765, float64 here: only used to pick the sample)
+    pts = wl.points.cpu().numpy().astype(np.float64)
+    vm = cam.world_view_transform.numpy().astype(np.float64)
+    pv = pts @ vm[:3, :3] + vm[3, :3]
+    fx, fy = sc.W / (2 * cam.tanfovx), sc.H / (2 * cam.tanfovy)
+    x = fx * pv[:, 0] / (pv[:, 2] + 1e-7) + sc.W / 2.0
+    y = fy * pv[:, 1] / (pv[:, 2] + 1e-7) + sc.H / 2.0
+    proj = (pv[:, 2] > 0.2) & (x >= 0) & (x < sc.W) & (y >= 0) & (y < sc.H)
+    keep = proj & (y < rows)
+    sample = np.ascontiguousarray(pts[keep][:2_000_000], np.float32)
+    PNs = int(sample.shape[0])
+    out = np.zeros((9, sc.H, sc.W), np.float32)
+    final_T = np.zeros((sc.H, sc.W), np.float32)
+    n_contrib = np.zeros((sc.H, sc.W), np.uint32)
+    alpha_int = np.ones(PNs, np.float32)
+    color_int = np.zeros((PNs, 3), np.float32)
+    _p = gof_oracle._p
+    t2 = time.perf_counter()
+    gof_oracle._lib.oracle_integrate(sc.W, sc.H, ctypes.c_float(sc.tan_fovx), ctypes.c_float(sc.tan_fovy), _p(sc.arr["viewmatrix"]), PNs,
+                                     _p(sample), _p(ranges_s), _p(np.ascontiguousarray(plist, np.uint32)),
+                                     _p(np.ascontiguousarray(g["rgb"], np.float32)), _p(np.ascontiguousarray(g["view2gaussian"], np.float32)),
+                                     _p(np.ascontiguousarray(g["conic_opacity"], np.float32)), _p(sc.arr["background"]), _p(out), _p(final_T),
+                                     _p(n_contrib), _p(alpha_int), _p(color_int))
+    t3 = time.perf_counter()
+    n_proj = int(proj.sum())
+    view_s = (t1 - t0) + (t3 - t2) * (n_proj / max(PNs, 1))
+    return {"kind": "port", "cores": gof_oracle.num_threads(), "host_cpus": os.cpu_count(), "gaussian_side_s": t1 - t0,
+            "sample_query_s": t3 - t2, "value": wl.PN / view_s, "unit": "points/s",
+            "sample": f"Gaussian side of the full view; point side on the {PNs} query points that project into the top {rows} pixel rows "
+                      f"(their tiles only), extrapolated to the {n_proj} projected points of the view"}
+
+
+def run_extract_reference(args, rank, world, dev):
+    import _util
+    import _refpy
+    ref = _util.load_ref()
+    pkg = _refpy.ref_rasterizer_package()
+    if ref is None or pkg is None:
+        return {"impl": "reference", "unavailable": "reference extension / staged Python not built here (needs /root/reference at build time)"}
+    wl = ExtractWorkload(args, dev, rank, world)
+    g = wl.gs
+    e = torch.Tensor([])
+
+    def step_device(s):
+        c = wl.cams[wl.view(s)]
+        vm, pm, cp = (c.world_view_transform.to(dev), c.full_proj_transform.to(dev), c.camera_center.to(dev))
+        return ref.integrate_gaussians_to_points(wl.bg, wl.points, g["means3D"], e, g["opacities"], g["scales"], g["rotations"], 1.0, e, e, vm,
+                                                 pm, c.tanfovx, c.tanfovy, 0.0, wl.subpix, wl.H, wl.W, g["shs"], 3, cp, False, False)
+
+    for s in range(args.warmup):
+        step_device(s)
+    barrier_sync(world)
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record()
+    barrier_sync(world)
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    sv = wl.view(args.warmup)
+    o = step_device(args.warmup)
+    Rg, PNv, Vg = int(o[0]), int(o[1][8].sum().item()), int((o[4] > 0).sum())
+    del o
+    e2e_ms = extract_e2e(args, wl, world, dev, pkg.GaussianRasterizer, pkg.GaussianRasterizationSettings)
+    val = world * args.steps * wl.PN / (ms * 1e-3)
+    return {
+        "metric": EXTRACT_METRIC, "impl": "reference", "value": val, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": EXTRACT_WORKLOAD_FMT.format(cfg=args.config, P=wl.P, PN=wl.PN, W=wl.W, H=wl.H, nv=wl.n_views),
+                   "stats_view": sv, "visible": Vg, "num_rendered": Rg, "points_projected": PNv,
+                   "reference": "unmodified diff-gaussian-rasterization of GOF compiled for sm_100a (oracle/build_ref.sh), on the GPU"},
+        "cpu_baseline": {"kind": "reference", "cores": 0, "value": val, "unit": "points/s",
+                         "sample": "the reference has no CPU path; this arm runs its own CUDA kernels on the same B200"},
+        "e2e": {"value": world * args.steps * wl.PN / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": 35 * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                "api": "reference's own GaussianRasterizer(settings).integrate; same harness as our arm (bench.extract_e2e)"},
+        "clocks": clocks,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -542,6 +830,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(gof_synth.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--points", type=int, default=0, help="C5: number of query points (default: the config's 50 M)")
+    ap.add_argument("--views", type=int, default=0, help="C5: number of views on the ring (default 64)")
+    ap.add_argument("--tets", type=int, default=0, help="C5: number of tetrahedra of the pipeline run (default 6.5 per point)")
+    ap.add_argument("--no-pipeline", action="store_true", help="C5: skip the one full extraction run (evaluate_alpha + marching tets + bisection)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 gradient exchange: the library's NVLink peer-memory kernel (p2p), NCCL's all-reduce (nccl), or auto = p2p for the world sizes it has been validated on (2 and 4), NCCL otherwise")
     args = ap.parse_args()
@@ -554,7 +846,13 @@ def main():
     os.dup2(2, 1)
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local if world > 1 else 0)
-    line = run_ours(args, rank, world, dev) if args.impl == "ours" else run_reference(args, rank, world, dev)
+    extract = "points" in gof_synth.CONFIGS[args.config]
+    if extract and args.steps == 50:
+        args.steps = 16          # a step is a 50 M-point query: keep the default run within minutes
+    if extract:
+        line = run_extract_ours(args, rank, world, dev) if args.impl == "ours" else run_extract_reference(args, rank, world, dev)
+    else:
+        line = run_ours(args, rank, world, dev) if args.impl == "ours" else run_reference(args, rank, world, dev)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     if rank == 0:

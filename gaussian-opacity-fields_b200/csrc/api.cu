@@ -450,6 +450,96 @@ extern "C" int gof_integrate(const gof_scene_t* s, int PN, const float* points3D
   char* pts = (char*)point_alloc(point_user, PL.bytes);
   char* pbin = (char*)point_binning_alloc(point_binning_user, PBL.bytes);
   if (!pts || !pbin) { gof_set_error("point allocator returned NULL"); return GOF_E_ALLOC; }
-  return gof_launch_integrate(s, v, PN, points3D, geom, GL, bin, BL, img, IL, pts, PL, pbin, PBL, out_color,
-                              out_alpha_integrated, out_color_integrated, st);
+  return gof_launch_integrate(s, v, PN, points3D, reinterpret_cast<const GofSplat*>(geom + GL.splat),
+                              reinterpret_cast<const uint32_t*>(bin + BL.point_list), reinterpret_cast<const uint2*>(img + IL.ranges),
+                              img, IL, pts, PL, pbin, PBL, out_color, out_alpha_integrated, out_color_integrated, st);
+}
+
+// ---- the Gaussian side of the query, once per view --------------------------------------------------------------
+// extract_mesh.py calls integrate for the same 64 views 10 times (evaluage_alpha on the tetrahedra vertices, 8 bisection
+// steps, optionally the colours: extract_mesh.py:56,92,107) and only the query points change: preprocess, depth sort,
+// instance emission and tile sort of the Gaussians are identical in every pass.  gof_integrate_prepare runs them once and
+// leaves what the query kernel reads -- records, tile ranges, per-tile lists -- in ONE compact cache buffer
+// (64 B/Gaussian + 4 B/instance); gof_integrate_cached is the point side alone.
+static int int_sm_count() {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  return sm_count;
+}
+
+extern "C" size_t gof_integrate_cache_bytes(int P, int width, int height, int num_rendered) {
+  if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return 0;
+  return gof_int_cache_layout((size_t)P, width, height, (size_t)num_rendered).bytes;
+}
+
+extern "C" int gof_integrate_prepare(const gof_scene_t* s, gof_alloc_fn geom_alloc, void* geom_user, gof_alloc_fn binning_alloc,
+                                     void* binning_user, gof_alloc_fn image_alloc, void* image_user, gof_alloc_fn cache_alloc,
+                                     void* cache_user, int* radii, int* num_rendered, void* stream) {
+  int rc = validate_scene(s);
+  if (rc != GOF_OK) return rc;
+  if (!geom_alloc || !binning_alloc || !image_alloc || !cache_alloc || !num_rendered || !radii) {
+    gof_set_error("integrate_prepare: NULL argument");
+    return GOF_E_INVALID;
+  }
+  *num_rendered = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GofView v = gof_make_view(s);
+  uint32_t R = 0;
+  char *geom = nullptr, *bin = nullptr, *img = nullptr;
+  const GofGeomLayout GL = gof_geom_layout((size_t)s->P);
+  const GofImageLayout IL = gof_image_layout(s->width, s->height);
+  if (s->P > 0) {
+    geom = (char*)geom_alloc(geom_user, GL.bytes);
+    img = (char*)image_alloc(image_user, IL.bytes);
+    if (!geom || !img) { gof_set_error("scratch allocator returned NULL"); return GOF_E_ALLOC; }
+    if ((rc = preprocess_sort_count(s, v, geom, GL, radii, st, &R)) != GOF_OK) return rc;
+  }
+  *num_rendered = (int)R;
+  const GofIntCacheLayout CL = gof_int_cache_layout((size_t)s->P, s->width, s->height, (size_t)R);
+  char* cache = (char*)cache_alloc(cache_user, CL.bytes);
+  if (!cache) { gof_set_error("cache allocator returned NULL"); return GOF_E_ALLOC; }
+  if (s->P == 0) { GOF_CUDA_OK(cudaMemsetAsync(cache + CL.ranges, 0, (size_t)v.tiles * 8, st)); return GOF_OK; }
+  const GofBinLayout BL = gof_bin_layout((size_t)R, s->width, s->height, /*with_masks=*/false);
+  bin = (char*)binning_alloc(binning_user, BL.bytes);
+  if (!bin && BL.bytes) { gof_set_error("binning allocator returned NULL"); return GOF_E_ALLOC; }
+  if ((rc = gof_bin_tiles(s->P, (size_t)R, v, geom, GL, bin, BL, img, IL, s->debug != 0, st)) != GOF_OK) return rc;
+  GOF_CUDA_OK(cudaMemcpyAsync(cache + CL.splat, geom + GL.splat, (size_t)s->P * sizeof(GofSplat), cudaMemcpyDeviceToDevice, st));
+  GOF_CUDA_OK(cudaMemcpyAsync(cache + CL.ranges, img + IL.ranges, (size_t)v.tiles * 8, cudaMemcpyDeviceToDevice, st));
+  if (R) GOF_CUDA_OK(cudaMemcpyAsync(cache + CL.point_list, bin + BL.point_list, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+  return GOF_OK;
+}
+
+extern "C" int gof_integrate_cached(const gof_scene_t* s, int PN, const float* points3D, const void* cache, int num_rendered,
+                                    gof_alloc_fn image_alloc, void* image_user, gof_alloc_fn point_alloc, void* point_user,
+                                    gof_alloc_fn point_binning_alloc, void* point_binning_user, float* out_color,
+                                    float* out_alpha_integrated, float* out_color_integrated, void* stream) {
+  if (!s || s->P < 0 || s->width <= 0 || s->height <= 0 || !s->viewmatrix || !s->background) {
+    gof_set_error("integrate_cached: scene needs P, width, height, tan_fov, viewmatrix, background");
+    return GOF_E_INVALID;
+  }
+  if (s->P == 0 || PN <= 0) return GOF_OK;
+  if (!cache || !image_alloc || !point_alloc || !point_binning_alloc || !points3D || !out_color || !out_alpha_integrated ||
+      !out_color_integrated || num_rendered < 0) {
+    gof_set_error("integrate_cached: NULL argument");
+    return GOF_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const GofView v = gof_make_view(s);
+  const GofIntCacheLayout CL = gof_int_cache_layout((size_t)s->P, s->width, s->height, (size_t)num_rendered);
+  const GofImageLayout IL = gof_image_layout(s->width, s->height);
+  char* img = (char*)image_alloc(image_user, IL.bytes);
+  const GofPointLayout PL = gof_point_layout((size_t)PN);
+  const GofPointBinLayout PBL = gof_point_bin_layout((size_t)PN, v.tiles, int_sm_count());
+  char* pts = (char*)point_alloc(point_user, PL.bytes);
+  char* pbin = (char*)point_binning_alloc(point_binning_user, PBL.bytes);
+  if (!img || !pts || !pbin) { gof_set_error("scratch allocator returned NULL"); return GOF_E_ALLOC; }
+  const char* c = (const char*)cache;
+  return gof_launch_integrate(s, v, PN, points3D, reinterpret_cast<const GofSplat*>(c + CL.splat),
+                              reinterpret_cast<const uint32_t*>(c + CL.point_list), reinterpret_cast<const uint2*>(c + CL.ranges), img,
+                              IL, pts, PL, pbin, PBL, out_color, out_alpha_integrated, out_color_integrated, st);
 }

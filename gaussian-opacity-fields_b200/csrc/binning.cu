@@ -82,22 +82,75 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
   return r;
 }
 
-// Decoupled look-back for ONE running quantity: publishes this chunk's aggregate, walks back over the predecessors'
-// status words until one carries an inclusive prefix, publishes the own inclusive prefix; returns the exclusive prefix.
-__device__ __forceinline__ uint32_t lookback(uint32_t* status, size_t stride, uint32_t chunk, uint32_t aggregate) {
+// Decoupled look-back: a chunk publishes its aggregate in a status word (flag | count, written and read as ONE word), walks
+// back over its predecessors' words until one carries an inclusive prefix, then publishes its own inclusive prefix.
+// Warp-wide variant for the scans (one running quantity per chunk, thousands of chunks in flight): the 32 lanes of a warp
+// fetch 32 consecutive predecessors in one coalesced request, so a walk over k predecessors costs k/32 dependent round
+// trips.  Called by ALL lanes of one warp; every lane returns the exclusive prefix.
+__device__ __forceinline__ uint32_t lookback_warp(uint32_t* status, uint32_t chunk, uint32_t aggregate) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) st_volatile(status + chunk, (chunk == 0 ? LB_INC : LB_AGG) | aggregate);
+  uint32_t excl = 0u;
+  int64_t pos = (int64_t)chunk;   // entries [0, pos) still to be examined; lane 0 takes the nearest
+  while (pos > 0) {
+    const int64_t idx = pos - 1 - lane;
+    uint32_t w;
+    do {
+      w = idx >= 0 ? ld_volatile(status + idx) : LB_INC;   // in front of chunk 0: an inclusive prefix of zero
+    } while (__any_sync(0xffffffffu, (w >> 30) == 0u));
+    const uint32_t inc = __ballot_sync(0xffffffffu, (w >> 30) == 2u);
+    const int first = inc ? __ffs(inc) - 1 : 31;       // nearest predecessor carrying an inclusive prefix
+    uint32_t v = lane <= first ? (w & LB_VAL) : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    excl += v;
+    if (inc) break;
+    pos -= 32;
+  }
+  if (lane == 0 && chunk != 0) st_volatile(status + chunk, LB_INC | (excl + aggregate));
+  return excl;
+}
+
+// The same for the radix passes, where 256 digits look back at once: the status words of one digit are CONTIGUOUS over the
+// chunks ([digit][chunk] layout), so one 128-bit volatile load fetches four predecessors.  With all chunks of a pass resident
+// at the same time a chunk has to walk back over about half of its predecessors before it meets an inclusive prefix; four at a
+// time quarters the number of dependent L2 round trips that walk costs.
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lookback_row(uint32_t* row /* this digit's status words, 16-byte aligned */, uint32_t chunk,
+                                                 uint32_t aggregate) {
   if (chunk == 0) {
-    st_volatile(status, LB_INC | aggregate);
+    st_volatile(row, LB_INC | aggregate);
     return 0u;
   }
-  st_volatile(status + (size_t)chunk * stride, LB_AGG | aggregate);
+  st_volatile(row + chunk, LB_AGG | aggregate);
   uint32_t excl = 0u;
-  for (int64_t c = (int64_t)chunk - 1; c >= 0; --c) {
-    uint32_t w;
-    do { w = ld_volatile(status + (size_t)c * stride); } while ((w >> 30) == 0u);
-    excl += w & LB_VAL;
-    if ((w >> 30) == 2u) break;
+  uint32_t pos = chunk;   // entries [0, pos) are still to be examined, from the top
+  while (pos > 0) {
+    const uint32_t g0 = (pos - 1u) & ~3u;
+    const uint32_t need = pos - g0;   // entries g0 .. g0+need-1 of this group
+    uint4 w;
+    bool ready;
+    do {
+      w = ld_volatile_v4(row + g0);
+      ready = (w.x >> 30) != 0u && (need < 2u || (w.y >> 30) != 0u) && (need < 3u || (w.z >> 30) != 0u) && (need < 4u || (w.w >> 30) != 0u);
+    } while (!ready);
+    const uint32_t e[4] = {w.x, w.y, w.z, w.w};
+    bool done = false;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      if (!done && (uint32_t)i < need) {
+        excl += e[i] & LB_VAL;
+        if ((e[i] >> 30) == 2u) done = true;
+      }
+    }
+    if (done) break;
+    pos = g0;
   }
-  st_volatile(status + (size_t)chunk * stride, LB_INC | (excl + aggregate));
+  st_volatile(row + chunk, LB_INC | (excl + aggregate));
   return excl;
 }
 
@@ -129,10 +182,11 @@ __global__ void __launch_bounds__(THREADS) k_digit_hist(const KeyT* __restrict__
 // One stable LSD radix pass in one launch.  Chunk c = keys [c*4096, (c+1)*4096); warp w of the CTA owns a contiguous
 // 1/8 of it, 32 keys per round: (chunk, warp, round, lane) order == input order, ranks within a digit follow it.
 template <typename KeyT>
-__global__ void __launch_bounds__(THREADS) k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-                                                     int shift, uint32_t mask, const uint32_t* __restrict__ ghist,
-                                                     uint32_t* __restrict__ status /* [chunks][256] */, uint32_t* __restrict__ ticket) {
+__global__ void __launch_bounds__(THREADS, 3) k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                        KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
+                                                        int shift, uint32_t mask, const uint32_t* __restrict__ ghist,
+                                                        uint32_t* __restrict__ status /* [256][stride] */, uint32_t stride,
+                                                        uint32_t* __restrict__ ticket) {
   __shared__ uint32_t s_cnt[WARPS][GOF_RADIX];   // per-warp digit counters -> exclusive offsets over the warps
   __shared__ uint32_t s_gbase[GOF_RADIX];        // global position of this chunk's first key of each digit
   __shared__ uint32_t s_lbase[GOF_RADIX];        // chunk-local position of the first key of each digit
@@ -150,20 +204,19 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const KeyT* __restrict__ k
   const size_t wbase = cbase + (size_t)warp * (ITEMS * 32);
 
   KeyT key[ITEMS];
-  uint32_t val[ITEMS];
   uint32_t rank[ITEMS];
+  // all 16 key loads of the thread are issued before the first one is used
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const size_t i = wbase + (size_t)r * 32 + lane;
+    key[r] = i < n ? keys_in[i] : (KeyT)0;
+  }
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const size_t i = wbase + (size_t)r * 32 + lane;
     const bool valid = i < n;
-    uint32_t d = GOF_RADIX;   // sentinel digit for the ragged tail
-    key[r] = 0; val[r] = 0;
-    if (valid) {
-      key[r] = keys_in[i];
-      val[r] = vals_in[i];
-      d = ((uint32_t)key[r] >> shift) & mask;
-    }
+    const uint32_t d = valid ? (((uint32_t)key[r] >> shift) & mask) : (uint32_t)GOF_RADIX;   // sentinel digit for the ragged tail
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
@@ -185,13 +238,13 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const KeyT* __restrict__ k
       s_cnt[w][threadIdx.x] = count;
       count += c;
     }
-    s_gbase[threadIdx.x] = gstart + lookback(status + threadIdx.x, GOF_RADIX, chunk, count);
   }
   uint32_t chunk_n;
   const uint32_t lstart = block_excl_scan(count, &chunk_n);   // barrier inside
   s_lbase[threadIdx.x] = lstart;
   __syncthreads();
-  // reorder the chunk in shared memory: digit runs become contiguous
+  // reorder the chunk in shared memory (digit runs become contiguous); the values are fetched only now -- they are not
+  // needed for ranking and 16 more live registers would cost a resident CTA per SM
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const size_t i = wbase + (size_t)r * 32 + lane;
@@ -199,9 +252,11 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const KeyT* __restrict__ k
       const uint32_t d = ((uint32_t)key[r] >> shift) & mask;
       const uint32_t lp = s_lbase[d] + s_cnt[warp][d] + rank[r];
       s_keys[lp] = key[r];
-      s_vals[lp] = val[r];
+      s_vals[lp] = vals_in[i];
     }
   }
+  // the look-back (dependent L2 round trips) overlaps the value loads above
+  if (threadIdx.x <= mask) s_gbase[threadIdx.x] = gstart + lookback_row(status + (size_t)threadIdx.x * stride, chunk, count);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
@@ -218,8 +273,9 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const KeyT* __restrict__ k
 
 struct SortScratch {
   uint32_t* ghist;     // [4][256]
-  uint32_t* tickets;   // [64]: [0..3] chunk tickets of the passes, [8] ticket of a fused scan
-  uint32_t* status;    // [4][chunks + 1][256]
+  uint32_t* tickets;   // [64]: [0..3] chunk tickets of the passes
+  uint32_t* status;    // [4][256][stride]: look-back status words, one row per digit
+  uint32_t stride;     // chunks rounded up to a multiple of 4, + 4
   size_t pass_words;   // words per pass in status
 };
 SortScratch carve_sort_scratch(uint32_t* scratch, size_t n) {
@@ -227,7 +283,8 @@ SortScratch carve_sort_scratch(uint32_t* scratch, size_t n) {
   s.ghist = scratch;
   s.tickets = scratch + 4 * GOF_RADIX;
   s.status = scratch + GOF_SORT_HEAD_BYTES / 4;
-  s.pass_words = (size_t)(gof_sort_blocks(n) + 1) * GOF_RADIX;
+  s.stride = (uint32_t)((gof_sort_blocks(n) + 3) / 4 * 4 + 4);
+  s.pass_words = (size_t)s.stride * GOF_RADIX;
   return s;
 }
 
@@ -251,7 +308,7 @@ int onesweep_passes(KeyT* ka, KeyT* kb, uint32_t* va, uint32_t* vb, size_t n, co
     const bool a2b = (p % 2 == 0);
     GOF_LAUNCH("radix_onesweep", st, k_onesweep<KeyT><<<nb, THREADS, 0, st>>>(
         a2b ? ka : kb, a2b ? va : vb, a2b ? kb : ka, a2b ? vb : va, n, dg.shift[p], dg.mask[p], sc.ghist + p * GOF_RADIX,
-        sc.status + (size_t)p * sc.pass_words, sc.tickets + p));
+        sc.status + (size_t)p * sc.pass_words, sc.stride, sc.tickets + p));
     GOF_LAUNCH_CHECK(debug, st);
   }
   return GOF_OK;
@@ -304,10 +361,12 @@ __global__ void __launch_bounds__(THREADS) k_scan_excl(const uint32_t* __restric
   }
   uint32_t total;
   uint32_t run = block_excl_scan(s, &total);
-  if (threadIdx.x == 0) {
-    const uint32_t excl = lookback(status, 1, chunk, total);
-    s_prefix = excl;
-    if (chunk == nchunks - 1 && total_out) *total_out = excl + total;
+  if (threadIdx.x < 32) {
+    const uint32_t excl = lookback_warp(status, chunk, total);
+    if (threadIdx.x == 0) {
+      s_prefix = excl;
+      if (chunk == nchunks - 1 && total_out) *total_out = excl + total;
+    }
   }
   __syncthreads();
   run += s_prefix;
@@ -350,9 +409,9 @@ __global__ void __launch_bounds__(THREADS) k_scan_emit(int P, const uint32_t* __
   uint32_t total;
   const uint32_t lo = block_excl_scan(n, &total);
   s_off[threadIdx.x] = lo; s_g[threadIdx.x] = g; s_rect[threadIdx.x] = rc;
-  if (threadIdx.x == 0) {
-    s_off[THREADS] = total;
-    s_prefix = lookback(status, 1, chunk, total);
+  if (threadIdx.x < 32) {
+    const uint32_t excl = lookback_warp(status, chunk, total);
+    if (threadIdx.x == 0) { s_off[THREADS] = total; s_prefix = excl; }
   }
   __syncthreads();
   const uint32_t prefix = s_prefix;

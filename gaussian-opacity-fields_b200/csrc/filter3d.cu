@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) k_filter3d_min(int P, const float* __rest
     __syncthreads();
     if ((int)threadIdx.x < stride) s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + stride]);
   }
+  __syncthreads();   // the load of s_max[0] below is hoisted in front of the thread test (racecheck: read by all threads)
   if (threadIdx.x == 0 && s_max[0] > 0.0f) atomicMax(dmax_bits, __float_as_uint(s_max[0]));   // positive floats order like uints
 }
 

@@ -180,7 +180,7 @@ static inline int gof_sort_blocks(size_t n) { return (int)((n + GOF_SORT_CHUNK -
 // GOF_BINNING=legacy, need 256 * (blocks + 1) words of it.)
 #define GOF_SORT_HEAD_BYTES (4 * GOF_RADIX * 4 + 256)
 static inline size_t gof_sort_scratch_bytes(size_t n) {
-  return (size_t)GOF_SORT_HEAD_BYTES + (size_t)4 * (size_t)(gof_sort_blocks(n) + 1) * GOF_RADIX * 4;
+  return (size_t)GOF_SORT_HEAD_BYTES + (size_t)4 * (size_t)(gof_sort_blocks(n) + 8) * GOF_RADIX * 4;
 }
 
 struct GofGeomLayout {      // "geomBuffer": everything sized by P
@@ -347,10 +347,21 @@ static inline GofPointBinLayout gof_point_bin_layout(size_t PN, int tiles, int s
   L.ids = take((size_t)L.nblk * 256 * GOF_INT_MAX_CONTRIB * 2);
   L.bytes = o; return L;
 }
-int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const float* points3D, const char* geom,
-                         const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL, char* img, const GofImageLayout& IL,
-                         char* pts, const GofPointLayout& PL, char* pbin, const GofPointBinLayout& PBL, float* out_color,
-                         float* out_alpha, float* out_color_int, cudaStream_t st);
+int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const float* points3D, const GofSplat* splat,
+                         const uint32_t* point_list, const uint2* ranges, char* img, const GofImageLayout& IL, char* pts,
+                         const GofPointLayout& PL, char* pbin, const GofPointBinLayout& PBL, float* out_color, float* out_alpha,
+                         float* out_color_int, cudaStream_t st);
+
+// Per-view cache of the Gaussian side of the opacity-field query (gof_integrate_prepare / gof_integrate_cached): the records,
+// the tile ranges and the per-tile Gaussian lists are all a query needs, and they do not depend on the query points.
+struct GofIntCacheLayout { size_t splat, ranges, point_list, bytes; };
+static inline GofIntCacheLayout gof_int_cache_layout(size_t P, int W, int H, size_t R) {
+  const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
+  GofIntCacheLayout L; size_t o = 0;
+  auto take = [&](size_t b) { size_t r = o; o = gof_align_up(o + b, 256); return r; };
+  L.splat = take(P * sizeof(GofSplat)); L.ranges = take(tiles * 8); L.point_list = take(R * 4); L.bytes = o;
+  return L;
+}
 
 // render_fwd.cu / render_bwd.cu
 int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char* geom,

@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, 3) k_integrate(const IntArgs a
 
 }  // namespace
 
-int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const float* points3D, const char* geom,
-                         const GofGeomLayout& GL, const char* bin, const GofBinLayout& BL, char* img, const GofImageLayout& IL,
-                         char* pts, const GofPointLayout& PL, char* pbin, const GofPointBinLayout& PBL, float* out_color,
-                         float* out_alpha, float* out_color_int, cudaStream_t st) {
+int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const float* points3D, const GofSplat* splat,
+                         const uint32_t* point_list, const uint2* ranges, char* img, const GofImageLayout& IL, char* pts,
+                         const GofPointLayout& PL, char* pbin, const GofPointBinLayout& PBL, float* out_color, float* out_alpha,
+                         float* out_color_int, cudaStream_t st) {
   const bool debug = s->debug != 0;
   PtArgs pa;
   pa.PN = PN; pa.W = v.W; pa.H = v.H; pa.grid_x = v.grid_x; pa.grid_y = v.grid_y; pa.tiles = v.tiles;
@@ -319,9 +319,9 @@ int gof_launch_integrate(const gof_scene_t* s, const GofView& v, int PN, const f
 
   IntArgs a;
   a.W = v.W; a.H = v.H; a.grid_x = v.grid_x; a.tiles = v.tiles; a.focal_x = v.focal_x; a.focal_y = v.focal_y;
-  a.ranges = reinterpret_cast<const uint2*>(img + IL.ranges);
-  a.point_list = reinterpret_cast<const uint32_t*>(bin + BL.point_list);
-  a.splat = reinterpret_cast<const GofSplat*>(geom + GL.splat);
+  a.ranges = ranges;
+  a.point_list = point_list;
+  a.splat = splat;
   a.pranges = pranges; a.pt_list = in_b ? vb : va; a.pt_xy = pa.xy; a.pt_depth = pa.depth; a.bg = s->background;
   a.ids = reinterpret_cast<uint16_t*>(pbin + PBL.ids);
   a.final_T = reinterpret_cast<float*>(img + IL.accum);

@@ -358,15 +358,20 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geo
   a.stats = gof_stats_buffer();
   static int occ = -1, stage = -1;   // GOF_BWD_OCC=2|3|4 (tuning knob); GOF_STAGE: staging variant (see render_fwd.cu)
   if (occ < 0) { const char* e = getenv("GOF_BWD_OCC"); occ = e ? atoi(e) : 4; }
-  if (stage < 0) { const char* e = getenv("GOF_STAGE"); stage = !e ? 1 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1)); }
+  if (stage < 0) {
+    const char* e = getenv("GOF_STAGE_BWD");
+    if (!e) e = getenv("GOF_STAGE");
+    stage = !e ? 1 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1));
+  }
   const size_t smem = (size_t)(stage ? 2 : 1) * BATCH * 96;
 #define GOF_BWD_LAUNCH(STATS, MINB, STG)                                                                                      \
   do {                                                                                                                        \
     static bool attr_set = false;                                                                                             \
     if (!attr_set) {                                                                                                          \
       GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BATCH * 96)); \
+      const int need = MINB * ((STG ? 2 : 1) * BATCH * 96 + 1024 + 128);   /* only what MINB CTAs need: the rest stays L1 */             \
       GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG>, cudaFuncAttributePreferredSharedMemoryCarveout,                \
-                                       (int)cudaSharedmemCarveoutMaxShared));                                                             \
+                                       (need * 100 + 233471) / 233472 > 100 ? 100 : (need * 100 + 233471) / 233472));                     \
       attr_set = true;                                                                                                        \
     }                                                                                                                         \
     GOF_LAUNCH("render_bwd", st, k_render_backward<STATS, MINB, STG><<<v.tiles, GOF_BLOCK_SIZE, smem, st>>>(a));             \

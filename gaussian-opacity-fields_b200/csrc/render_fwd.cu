@@ -288,13 +288,18 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
   a.vstride = BL.vmask_stride;
   static int occ = -1, stage = -1;   // GOF_FWD_OCC=3|4: resident CTAs per SM the kernel is compiled for; GOF_STAGE: staging variant
   if (occ < 0) { const char* e = getenv("GOF_FWD_OCC"); occ = e ? atoi(e) : 4; }
-  if (stage < 0) { const char* e = getenv("GOF_STAGE"); stage = !e ? 1 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1)); }
+  if (stage < 0) {
+    const char* e = getenv("GOF_STAGE_FWD");
+    if (!e) e = getenv("GOF_STAGE");
+    stage = !e ? 1 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1));
+  }
 #define GOF_FWD_LAUNCH(MINB, STG)                                                                                              \
   do {                                                                                                                        \
-    static bool attr_set = false;   /* 4 CTAs x 40 KB of staging buffers per SM: ask for the large shared-memory carveout */   \
-    if (!attr_set) {                                                                                                          \
+    static bool attr_set = false;   /* MINB CTAs x (20 or 40 KB + 1 KB) per SM: ask for just that much shared memory --      */ \
+    if (!attr_set) {                /* the rest stays L1 (local-memory spills and the mask / output traffic go through it)    */ \
+      const int need = MINB * ((STG ? 2 : 1) * BATCH * 80 + 1024 + 64);                                                       \
       GOF_CUDA_OK(cudaFuncSetAttribute(k_render_forward<MINB, STG>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
-                                       (int)cudaSharedmemCarveoutMaxShared));                                                \
+                                       (need * 100 + 233471) / 233472 > 100 ? 100 : (need * 100 + 233471) / 233472));        \
       attr_set = true;                                                                                                        \
     }                                                                                                                         \
     GOF_LAUNCH("render_fwd", st, k_render_forward<MINB, STG><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));                        \

@@ -272,7 +272,12 @@ int gof_marching_tets_emit(int num_verts, const float* sdf, int64_t num_tets, co
     return GOF_E_INVALID;
   }
   EmitArgs a;
-  a.T = num_tets; a.chunk = (chunk_tets > 0 && num_tets > chunk_tets) ? (num_tets + (num_tets / chunk_tets + 1) - 1) / (num_tets / chunk_tets + 1) : num_tets;
+  // rows per chunk: the reference splits with torch.chunk(tets, T // chunk_size + 1) (utils/tetmesh.py:56-58), i.e. ceil(T / n)
+  // rows; a NEGATIVE chunk_tets states the rows per chunk directly (tet-sharded extraction: every shard must cut where the
+  // unsharded call cuts)
+  a.T = num_tets;
+  if (chunk_tets < 0) a.chunk = -chunk_tets;
+  else a.chunk = (chunk_tets > 0 && num_tets > chunk_tets) ? (num_tets + (num_tets / chunk_tets + 1) - 1) / (num_tets / chunk_tets + 1) : num_tets;
   a.tets = tets; a.code = (unsigned char*)(S + L.code);
   a.cross_off = (uint32_t*)(S + L.cross_off); a.f1_off = (uint32_t*)(S + L.f1_off); a.f2_off = (uint32_t*)(S + L.f2_off);
   a.inst_uid = (uint32_t*)(S + L.inst_uid); a.lo = (uint32_t*)(S + L.lo_b); a.hi = (uint32_t*)(S + L.hi);

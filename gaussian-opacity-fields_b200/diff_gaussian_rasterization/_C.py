@@ -337,6 +337,70 @@ def integrate_gaussians_to_points(background, points3D, means3D, colors, opacity
     return rendered.value, out_color, alpha_int, color_int, radii, geom.tensor, binning.tensor, img.tensor
 
 
+_lib.gof_integrate_cache_bytes.restype = ctypes.c_size_t
+_lib.gof_integrate_cache_bytes.argtypes = [ctypes.c_int] * 4
+_lib.gof_integrate_prepare.restype = ctypes.c_int
+_lib.gof_integrate_prepare.argtypes = [ctypes.POINTER(_Scene)] + [_ALLOC_FN, ctypes.c_void_p] * 4 + [_fp, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+_lib.gof_integrate_cached.restype = ctypes.c_int
+_lib.gof_integrate_cached.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int, _fp, _fp, ctypes.c_int] + [_ALLOC_FN, ctypes.c_void_p] * 3 + \
+    [_fp, _fp, _fp, ctypes.c_void_p]
+
+
+class IntegrateCache:
+    """Gaussian side of one view of the opacity-field query (gof_integrate_prepare): records + tile ranges + tile lists in one
+    uint8 CUDA tensor.  Opaque; pass it to integrate_points_cached."""
+
+    def __init__(self, buffer, num_rendered, radii, P, H, W):
+        self.buffer, self.num_rendered, self.radii, self.P, self.H, self.W = buffer, num_rendered, radii, P, H, W
+
+    @property
+    def nbytes(self):
+        return self.buffer.numel()
+
+
+def integrate_prepare(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, view2gaussian_precomp,
+                      viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset, image_height, image_width, sh, degree,
+                      campos, prefiltered, debug):
+    """Gaussian side of integrate_gaussians_to_points for one view (same arguments minus points3D) -> IntegrateCache."""
+    keep = []
+    s = _scene(keep, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, view2gaussian_precomp,
+               viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset, image_height, image_width, sh, degree, campos,
+               prefiltered, debug)
+    dev = means3D.device
+    radii = torch.zeros((s.P,), dtype=torch.int32, device=dev)
+    geom, binning, img = _Scratch(dev, "geom"), _Scratch(dev, "binning", 1.25), _Scratch(dev, "image")
+    cache = _Scratch(dev)          # not pooled: the cache outlives the call
+    rendered = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        _check(_lib.gof_integrate_prepare(ctypes.byref(s), geom.cb, None, binning.cb, None, img.cb, None, cache.cb, None,
+                                          radii.data_ptr(), ctypes.byref(rendered), _stream()))
+    return IntegrateCache(cache.tensor, rendered.value, radii, s.P, int(image_height), int(image_width))
+
+
+def integrate_points_cached(cache, background, points3D, viewmatrix, tan_fovx, tan_fovy, debug=False):
+    """Point side of integrate_gaussians_to_points against an IntegrateCache of the same view.
+    Returns (out_color[9,H,W], out_alpha_integrated[PN], out_color_integrated[PN,3])."""
+    if points3D.ndimension() != 2 or points3D.size(1) != 3:
+        raise RuntimeError("points3D must have dimensions (num_points, 3)")
+    dev = cache.buffer.device
+    s = _Scene()
+    s.P, s.width, s.height = cache.P, cache.W, cache.H
+    s.tan_fovx, s.tan_fovy = float(tan_fovx), float(tan_fovy)
+    bg, vm, p3 = _c(background), _c(viewmatrix), _c(points3D)
+    s.background, s.viewmatrix, s.debug = _ptr(bg, device=dev), _ptr(vm, device=dev), int(bool(debug))
+    PN = p3.size(0)
+    out_color = torch.zeros((9, cache.H, cache.W), dtype=torch.float32, device=dev)
+    alpha_int = torch.ones((PN,), dtype=torch.float32, device=dev)
+    color_int = torch.zeros((PN, 3), dtype=torch.float32, device=dev)
+    img, pts, pbin = _Scratch(dev, "image"), _Scratch(dev, "points"), _Scratch(dev, "point_binning")
+    if cache.P != 0 and PN != 0:
+        with torch.cuda.device(dev):
+            _check(_lib.gof_integrate_cached(ctypes.byref(s), PN, _ptr(p3, device=dev), cache.buffer.data_ptr(), cache.num_rendered, img.cb,
+                                             None, pts.cb, None, pbin.cb, None, out_color.data_ptr(), alpha_int.data_ptr(),
+                                             color_int.data_ptr(), _stream()))
+    return out_color, alpha_int, color_int
+
+
 def export_state(P, W, H, num_rendered, geomBuffer, binningBuffer, imgBuffer, radii):
     """Parity-test helper (gof_export_state): this library's scratch buffers in the reference's field layout."""
     dev = radii.device

@@ -83,8 +83,60 @@ CONFIGS = {
     "C1": dict(P=10_000, width=256, height=256, seed=0),
     "C2": dict(P=200_000, width=800, height=800, seed=1),
     "C3": dict(P=1_000_000, width=1920, height=1080, seed=2),
-    "C4": dict(P=2_500_000, width=1920, height=1080, seed=3),
+    "C4": dict(P=2_500_000, width=1920, height=1080, seed=3, appearance=True),
+    # mesh extraction: 3 M Gaussians, 50 M tetrahedra vertices (query points), 64 views, ~6.5 tets per point
+    "C5": dict(P=3_000_000, width=1920, height=1080, seed=4, points=50_000_000, tets_per_point=6.5, n_views=64),
 }
+
+
+def make_tetra_points(gs, n_points, seed, device):
+    """Query points of the extraction workload, generated ON `device`: like GaussianModel.get_tetra_points
+    (scene/gaussian_model.py:433-463) the 8 corners of every Gaussian's 3-sigma box plus its centre (9 P points), topped up
+    to `n_points` with points drawn uniformly inside the 3-sigma boxes.  Points of one Gaussian are contiguous, so nearby
+    indices are nearby in space.  Returns (points [n,3], scale [n,1])."""
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    xyz, scales, q = gs["means3D"].to(device), gs["scales"].to(device), gs["rotations"].to(device)
+    P = xyz.shape[0]
+    r, x, y, z = q.unbind(1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).view(P, 3, 3)
+    corners = torch.tensor([[sx, sy, sz] for sx in (-1.0, 1.0) for sy in (-1.0, 1.0) for sz in (-1.0, 1.0)], device=device)   # [8,3]
+    per = max(int(n_points) // P, 1)
+    n_rand = max(per - 9, 0)
+    parts = []
+    if per >= 9:
+        local = torch.cat([corners[None].expand(P, 8, 3), torch.zeros(P, 1, 3, device=device)], dim=1)
+        if n_rand:
+            local = torch.cat([local, torch.rand(P, n_rand, 3, generator=g, device=device) * 2 - 1], dim=1)
+    else:
+        local = torch.rand(P, per, 3, generator=g, device=device) * 2 - 1
+    k = local.shape[1]
+    pts = torch.einsum("pij,pkj->pki", R, local * (3.0 * scales)[:, None, :]) + xyz[:, None, :]
+    parts.append(pts.reshape(-1, 3))
+    sc = (3.0 * scales).amax(dim=1, keepdim=True)[:, None, :].expand(P, k, 1).reshape(-1, 1)
+    points = parts[0]
+    if points.shape[0] < n_points:          # remainder: extra samples around the first Gaussians
+        m = int(n_points) - points.shape[0]
+        idx = torch.arange(m, device=device) % P
+        extra = torch.einsum("pij,pj->pi", R[idx], (torch.rand(m, 3, generator=g, device=device) * 2 - 1) * 3.0 * scales[idx]) + xyz[idx]
+        points = torch.cat([points, extra])
+        sc = torch.cat([sc, (3.0 * scales[idx]).amax(dim=1, keepdim=True)])
+    return points[:n_points].contiguous(), sc[:n_points].contiguous()
+
+
+def make_local_tets(n_points, n_tets, seed, device):
+    """Synthetic tetrahedralisation of the query points for the marching-tetrahedra workload (CGAL's Delaunay, the
+    reference's tet source, is a single-threaded CPU library that is not part of this image): every tet joins a vertex with
+    three others at most 17 indices away -- the point cluster of the same Gaussian (make_tetra_points keeps it contiguous) or
+    of its index neighbour -- so that tets are small and the gather locality resembles a Delaunay mesh of the same size.
+    int64 [n_tets, 4], generated on `device`."""
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    a = torch.randint(0, int(n_points), (int(n_tets),), generator=g, device=device)
+    o1 = torch.randint(1, 4, (int(n_tets),), generator=g, device=device)
+    o2 = torch.randint(4, 10, (int(n_tets),), generator=g, device=device)
+    o3 = torch.randint(10, 18, (int(n_tets),), generator=g, device=device)
+    return torch.stack([a, (a + o1) % n_points, (a + o2) % n_points, (a + o3) % n_points], dim=1).contiguous()
 
 
 def make_scene(name_or_cfg, view=0, device="cpu", **overrides):

@@ -26,7 +26,18 @@ _lib.gof_marching_tets_emit.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_
 CHUNK_TETS = 32 * 1024 * 1024   # utils/tetmesh.py:55
 
 
-def _unbatched_marching_tetrahedra(vertices, tets, sdf, scales, chunk_tets=CHUNK_TETS):
+def chunk_rows(num_tets, chunk_tets=CHUNK_TETS):
+    """Rows per chunk of the reference's split: torch.chunk(tets, T // chunk_size + 1) (utils/tetmesh.py:56-58)."""
+    if chunk_tets <= 0 or num_tets <= chunk_tets:
+        return max(int(num_tets), 1)
+    n = num_tets // chunk_tets + 1
+    return -(-num_tets // n)
+
+
+def _unbatched_marching_tetrahedra(vertices, tets, sdf, scales, chunk_tets=CHUNK_TETS, rows=None):
+    """`rows`: rows per chunk stated directly (overrides the reference's rule applied to chunk_tets; see gof_extract)."""
+    if rows is not None:
+        chunk_tets = -int(rows)
     if not (vertices.is_cuda and tets.is_cuda and sdf.is_cuda and scales.is_cuda):
         raise RuntimeError("gof_b200 marching_tetrahedra: CUDA tensors required (no CPU path)")
     dev = vertices.device

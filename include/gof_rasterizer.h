@@ -115,6 +115,23 @@ GOF_API int gof_integrate(const gof_scene_t* scene, int PN, const float* points3
                   float* out_alpha_integrated, float* out_color_integrated,
                   int* num_rendered, void* stream);
 
+/* The same query with the Gaussian side cached per view.  extract_mesh.py:56,92,107 calls integrate for the SAME views ten
+ * times (tetrahedra vertices, 8 bisection steps, colours) -- only points3D changes, so preprocess / depth sort / instance
+ * emission / tile sort of the Gaussians (rasterizer_impl.cu:566-660) are identical in every pass.
+ *   gof_integrate_prepare: runs them once; `cache_alloc` is called once with gof_integrate_cache_bytes(P, W, H, *num_rendered)
+ *                          and receives records, tile ranges and per-tile lists (64 B/Gaussian + 4 B/instance + 8 B/tile);
+ *                          geom / binning / image buffers are scratch that may be released after the call; radii [P] out.
+ *   gof_integrate_cached:  the point side alone (rasterizer_impl.cu:662-792) against such a cache; of `scene` only P, width,
+ *                          height, tan_fovx/y, viewmatrix, background and debug are read.  Outputs as gof_integrate. */
+GOF_API size_t gof_integrate_cache_bytes(int P, int width, int height, int num_rendered);
+GOF_API int gof_integrate_prepare(const gof_scene_t* scene, gof_alloc_fn geom_alloc, void* geom_user,
+                  gof_alloc_fn binning_alloc, void* binning_user, gof_alloc_fn image_alloc, void* image_user,
+                  gof_alloc_fn cache_alloc, void* cache_user, int* radii, int* num_rendered, void* stream);
+GOF_API int gof_integrate_cached(const gof_scene_t* scene, int PN, const float* points3D, const void* cache, int num_rendered,
+                  gof_alloc_fn image_alloc, void* image_user, gof_alloc_fn point_alloc, void* point_user,
+                  gof_alloc_fn point_binning_alloc, void* point_binning_user, float* out_color,
+                  float* out_alpha_integrated, float* out_color_integrated, void* stream);
+
 /* Rasterizer::markVisible (rasterizer_impl.cu:174-186) == _C.mark_visible.  present: [P] bytes (bool). */
 GOF_API int gof_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present, void* stream);
@@ -144,7 +161,9 @@ GOF_API int gof_export_state(int P, int width, int height, int num_rendered,
  * Two phases because the output sizes are data dependent: `count` classifies the tets, emits and sorts the crossing
  * edges and returns the number of unique crossing edges E and of faces F on the host; `emit` then fills
  * caller-allocated outputs.  `chunk_tets` reproduces the reference's chunked face order (its chunk_size of
- * 32*1024*1024, tetmesh.py:55); pass 0 for "one chunk".  tets: [T,4] int64 vertex ids < 2^32.  Outputs:
+ * 32*1024*1024, tetmesh.py:55: the tets are cut into T / chunk_tets + 1 pieces of ceil(T / pieces) rows); pass 0 for "one
+ * chunk", or a NEGATIVE value -r to state r rows per chunk directly (used when the tets are sharded over ranks: every shard
+ * must cut where the unsharded call cuts).  tets: [T,4] int64 vertex ids < 2^32.  Outputs:
  * interp_v [E,2] int64 (sorted unique crossing edges), faces [F,3] int64; optional gathers of the edge endpoints:
  * edge_pos [E,2,3] from vertices [V,3], edge_sdf [E,2], edge_scales [E,2] from scales [V] (any may be NULL). */
 GOF_API int gof_marching_tets_count(int num_verts, const float* sdf, int64_t num_tets, const int64_t* tets, int64_t chunk_tets,
