@@ -80,11 +80,32 @@ def dist_setup(n):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "INFO")                       # which algorithm / transport NCCL picked goes into the JSON line
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/gof_nccl_%p.log")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(0)
     return rank, world, local
+
+
+def nccl_info():
+    """A few lines of NCCL's own INFO log of this process (which transports / algorithms it set up: NVLS, P2P, rings)."""
+    path = os.environ.get("NCCL_DEBUG_FILE", "").replace("%p", str(os.getpid()))
+    try:
+        keep = []
+        for ln in open(path, errors="replace"):
+            if any(k in ln for k in ("NVLS", "nvls", "Channel 00", "Connected all", "comm 0x", "via P2P")):
+                keep.append(ln.strip()[-160:])
+        seen, out = set(), []
+        for ln in keep:
+            key = ln.split("] ")[-1][:60]
+            if key not in seen:
+                seen.add(key); out.append(ln)
+        return out[:8]
+    except Exception:
+        return None
 
 
 def barrier_sync(world):
@@ -254,17 +275,20 @@ def run_ours(args, rank, world, dev):
     wl = Workload(args.config, dev, rank, world)
     bucket = gof_dp.GradBucket(wl.P, 16, dev)
     exchange_note = None
-    if world > 1 and (args.exchange == "p2p" or (args.exchange == "auto" and world in (2, 4))):
-        try:
-            bucket.enable_peer_exchange()
-        except Exception as e:   # e.g. no peer access between the GPUs of this box: say so and use NCCL
-            exchange_note = f"peer mapping failed ({type(e).__name__}: {e}); NCCL all-reduce used"
-            ok = torch.tensor([0.0], device=dev)
-        else:
-            ok = torch.tensor([1.0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) == 0.0:
-            bucket.exchange = "nccl"
+    if world > 1 and args.exchange != "nccl":
+        # every enable_* call is collective and fails on all ranks alike (it ends with an agreement all-reduce and a self-test
+        # on the live mapping), so the fallback chain below takes the same branch everywhere
+        order = {"auto": ("nvls", "p2p"), "nvls": ("nvls",), "p2p": ("p2p",)}[args.exchange]
+        notes = []
+        for mode in order:
+            try:
+                bucket.enable_nvls_exchange() if mode == "nvls" else bucket.enable_peer_exchange()
+                break
+            except Exception as e:   # noqa: BLE001 -- e.g. no multicast / no peer access on this box: say so and fall back
+                notes.append(f"{mode} unavailable ({type(e).__name__}: {str(e)[:160]})")
+        if notes:
+            exchange_note = "; ".join(notes) + (f"; using {bucket.exchange}" if bucket.exchange != "nccl" else "; NCCL all-reduce used")
+
     def step_device(step):
         v = wl.view(step)
         fa = wl.fwd_args(v)
@@ -272,13 +296,35 @@ def run_ours(args, rank, world, dev):
         bucket.zero_()
         grads = _C.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, wl.dL), _out=bucket.views)
         if world > 1:
-            bucket.all_reduce()
-            gof_dp.all_reduce_densification_stats(gof_dp.densification_stats(grads[0], radii))
+            bucket.all_reduce()      # gradients (SUM) and this step's densification statistics (SUM | MAX tail) in ONE exchange
         return color
 
     # ---- kernel-path throughput: inputs resident in HBM, CUDA events, max over ranks --------------------------
     for s in range(args.warmup):
         step_device(s)
+    exchange_check = None
+    if world > 1:   # untimed: the exchanged bucket equals the combination of the per-rank single-GPU results
+        fa = wl.fwd_args(wl.view(0))
+        R0, _c0, radii0, geom0, bin0, img0 = _C.rasterize_gaussians(*fa)
+        bucket.zero_()
+        _C.rasterize_gaussians_backward(*bwd_args(fa, radii0, geom0, R0, bin0, img0, wl.dL), _out=bucket.views)
+        local = bucket.flat.clone()
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        bucket.all_reduce()
+        ns = bucket.n_sum
+        want_sum = torch.stack([p[:ns] for p in parts]).double().sum(0)
+        mag = torch.stack([p[:ns] for p in parts]).double().abs().sum(0)
+        want_max = torch.stack([p[ns:] for p in parts]).amax(0)
+        err = float(((bucket.flat[:ns].double() - want_sum).abs() / (1e-6 * mag + 1e-30)).max())      # <= 1: within 1e-6 of the magnitude sum
+        ok_sum, ok_max = err <= 1.0, bool(torch.equal(bucket.flat[ns:], want_max))
+        same = torch.tensor([float(bucket.flat.double().sum())], dtype=torch.float64, device=dev)
+        lo, hi = same.clone(), same.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        flag = torch.tensor([1.0 if (ok_sum and ok_max and float(lo) == float(hi)) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_check = "ok" if float(flag.item()) == 1.0 else f"FAILED (sum err {err:.3g}, max ok {ok_max}, identical on ranks {float(lo) == float(hi)})"
+        del parts, local, want_sum, mag, want_max, geom0, bin0, img0
     barrier_sync(world)
     launches0 = _C.launch_count()
     sampler = ClockSampler(torch.cuda.current_device())
@@ -371,9 +417,15 @@ def run_ours(args, rank, world, dev):
         "kernels_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
     if allreduce_ms is not None:
-        what = ("sum of 59 f32 per Gaussian by the library's kernel over NVLink peer memory (csrc/exchange.cu), two NCCL barriers"
-                if bucket.exchange == "p2p" else "all-reduce(SUM) of 59 f32 per Gaussian (NCCL)")
-        line["exchange"] = {"impl": bucket.exchange, "what": what, "bytes": int(wl.P) * 59 * 4, "ms": allreduce_ms}
+        what = {"p2p": "59 gradient + 5 statistics f32 per Gaussian by the library's kernel over NVLink peer memory (csrc/exchange.cu), two NCCL barriers",
+                "nvls": "59 gradient + 5 statistics f32 per Gaussian reduced inside the NVSwitch by the library's multimem kernel "
+                        "(csrc/exchange.cu: multimem.ld_reduce + multimem.st on a symmetric-memory bucket), two NCCL barriers",
+                "nccl": "all-reduce(SUM) of 59 gradient + 3 statistics f32 per Gaussian and all-reduce(MAX) of 2 (NCCL)"}[bucket.exchange]
+        line["exchange"] = {"impl": bucket.exchange, "what": what, "bytes": int(bucket.nbytes), "ms": allreduce_ms}
+        line["exchange_check"] = exchange_check
+        info = nccl_info()
+        if info:
+            line["exchange"]["nccl_info"] = info
         if exchange_note:
             line["exchange"]["note"] = exchange_note
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -834,8 +886,10 @@ def main():
     ap.add_argument("--views", type=int, default=0, help="C5: number of views on the ring (default 64)")
     ap.add_argument("--tets", type=int, default=0, help="C5: number of tetrahedra of the pipeline run (default 6.5 per point)")
     ap.add_argument("--no-pipeline", action="store_true", help="C5: skip the one full extraction run (evaluate_alpha + marching tets + bisection)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="N>1 gradient exchange: the library's NVLink peer-memory kernel (p2p), NCCL's all-reduce (nccl), or auto = p2p for the world sizes it has been validated on (2 and 4), NCCL otherwise")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "p2p", "nccl"],
+                    help="N>1 gradient exchange: the library's multimem kernel through the NVSwitch (nvls), its NVLink peer-memory kernel "
+                         "(p2p), NCCL's all-reduce (nccl), or auto = nvls, else p2p, else nccl -- each mode is adopted only after a "
+                         "collective self-test on the live mapping")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():

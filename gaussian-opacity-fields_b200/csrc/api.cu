@@ -298,6 +298,16 @@ extern "C" int gof_rasterize_backward(const gof_scene_t* s, int num_rendered, co
                                       float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
                                       float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                                       float* dL_dview2gaussian, void* stream) {
+  return gof_rasterize_backward_stats(s, num_rendered, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dmean2D, dL_dconic,
+                                      dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview2gaussian,
+                                      nullptr, nullptr, stream);
+}
+
+extern "C" int gof_rasterize_backward_stats(const gof_scene_t* s, int num_rendered, const int* radii, void* geom_buffer,
+                                            const void* binning_buffer, const void* image_buffer, const float* dL_dpix,
+                                            float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                                            float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                            float* dL_dview2gaussian, float* dens_sum, float* dens_max, void* stream) {
   (void)dL_dconic; (void)dL_dcov3D;
   int rc = validate_scene(s);
   if (rc != GOF_OK) return rc;
@@ -324,7 +334,7 @@ extern "C" int gof_rasterize_backward(const gof_scene_t* s, int num_rendered, co
                                        st)) != GOF_OK)
     return rc;
   return gof_launch_preprocess_backward(s, v, geom, GL, radii, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dview2gaussian, dL_dmean3D,
-                                        dL_dsh, dL_dscale, dL_drot, st);
+                                        dL_dsh, dL_dscale, dL_drot, dens_sum, dens_max, st);
 }
 
 extern "C" int gof_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -18,28 +18,63 @@ struct PeerPtrs { float4* p[GOF_MAX_PEERS]; };
 
 __device__ __forceinline__ float4 ld_cg(const float4* p) { return __ldcg(p); }   // L2 only: peer data is never L1-cached
 
+// elements [begin, end) of this rank's slice; float4 index < sum_end: SUM over ranks, otherwise MAX (the densification
+// statistics max_radii2D / xyz_gradient_accum_abs_max ride in the tail of the same bucket)
+__device__ __forceinline__ float4 combine(const float4 s, const float4 v, bool is_sum) {
+  return is_sum ? make_float4(s.x + v.x, s.y + v.y, s.z + v.z, s.w + v.w)
+                : make_float4(fmaxf(s.x, v.x), fmaxf(s.y, v.y), fmaxf(s.z, v.z), fmaxf(s.w, v.w));
+}
+
 template <int W>
-__global__ void __launch_bounds__(512) k_p2p_allreduce(const PeerPtrs a, size_t begin, size_t end) {
+__global__ void __launch_bounds__(512) k_p2p_allreduce(const PeerPtrs a, size_t begin, size_t end, size_t sum_end) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
     float4 v[W];
 #pragma unroll
     for (int r = 0; r < W; ++r) v[r] = ld_cg(a.p[r] + i);
     float4 s = v[0];
+    const bool is_sum = i < sum_end;
 #pragma unroll
-    for (int r = 1; r < W; ++r) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    for (int r = 1; r < W; ++r) s = combine(s, v[r], is_sum);
 #pragma unroll
     for (int r = 0; r < W; ++r) __stcg(a.p[r] + i, s);
   }
 }
 
 // generic world size (3, 5, 6, 7): same scheme, runtime loop
-__global__ void __launch_bounds__(512) k_p2p_allreduce_any(const PeerPtrs a, int world, size_t begin, size_t end) {
+__global__ void __launch_bounds__(512) k_p2p_allreduce_any(const PeerPtrs a, int world, size_t begin, size_t end, size_t sum_end) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
     float4 s = ld_cg(a.p[0] + i);
-    for (int r = 1; r < world; ++r) { const float4 v = ld_cg(a.p[r] + i); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    const bool is_sum = i < sum_end;
+    for (int r = 1; r < world; ++r) s = combine(s, ld_cg(a.p[r] + i), is_sum);
     for (int r = 0; r < world; ++r) __stcg(a.p[r] + i, s);
+  }
+}
+
+// ---- the same exchange through the NVSwitch (NVLS): `mc` is the MULTICAST address of the bucket (every rank's copy bound to
+// one multicast object at the same offset).  multimem.ld_reduce pulls the 16 bytes at that offset from ALL ranks and hands
+// back their sum -- reduced inside the switch -- and multimem.st pushes the result to all of them: per GPU one bucket's worth of
+// NVLink traffic in each direction instead of 2 (N-1)/N buckets over peer loads/stores.  Rank r handles the r-th 1/N slice; the
+// MAX tail holds non-negative floats, whose bit patterns order like unsigned integers (f32 has no multimem max).
+__global__ void __launch_bounds__(512) k_nvls_allreduce(float4* mc, size_t begin, size_t end, size_t sum_end) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    float4* p = mc + i;
+    if (i < sum_end) {
+      float4 v;
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    } else {
+      uint32_t* q = reinterpret_cast<uint32_t*>(p);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t u;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(u) : "l"(q + k) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(q + k), "r"(u) : "memory");
+      }
+    }
   }
 }
 
@@ -92,8 +127,37 @@ extern "C" GOF_API int gof_peer_free(void* ptr) { if (ptr) GOF_CUDA_OK(cudaFree(
 // peers[r] = address (in THIS process) of rank r's bucket, r = 0..world-1; n = floats per bucket (multiple of 4,
 // 16-byte aligned buffers).  Reduces this rank's slice; the caller provides the two cross-rank barriers.
 extern "C" GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, size_t n, void* stream) {
-  if (!peers || world < 1 || world > GOF_MAX_PEERS || rank < 0 || rank >= world || (n & 3u)) {
-    gof_set_error("p2p_allreduce: bad arguments (world 1..8, n multiple of 4)");
+  return gof_p2p_allreduce_f32(peers, world, rank, n, n, stream);
+}
+
+static unsigned exchange_grid(size_t items) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const size_t want = (items + 511) / 512;
+  return (unsigned)(want < (size_t)sms * 4 ? want : (size_t)sms * 4);
+}
+
+// mc: multicast address of the bucket (valid in THIS process); n floats, the first n_sum summed, the rest max-reduced as
+// non-negative floats; n and n_sum multiples of 4.  The caller brackets the call with two cross-rank barriers on `stream`.
+extern "C" GOF_API int gof_nvls_allreduce_f32(float* mc, int world, int rank, size_t n_sum, size_t n, void* stream) {
+  if (!mc || world < 1 || rank < 0 || rank >= world || (n & 3u) || (n_sum & 3u) || n_sum > n || (reinterpret_cast<uintptr_t>(mc) & 15u)) {
+    gof_set_error("nvls_allreduce: bad arguments");
+    return GOF_E_INVALID;
+  }
+  if (world == 1 || n == 0) return GOF_OK;
+  const size_t n4 = n / 4;
+  const size_t begin = n4 * (size_t)rank / (size_t)world, end = n4 * (size_t)(rank + 1) / (size_t)world;
+  if (end <= begin) return GOF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  GOF_LAUNCH("nvls_allreduce", st, k_nvls_allreduce<<<exchange_grid(end - begin), 512, 0, st>>>(reinterpret_cast<float4*>(mc), begin, end, n_sum / 4));
+  GOF_LAUNCH_CHECK(false, st);
+  return GOF_OK;
+}
+
+// the first n_sum floats are summed over the ranks, the remaining n - n_sum max-reduced (n_sum == n: plain sum)
+extern "C" GOF_API int gof_p2p_allreduce_f32(float* const* peers, int world, int rank, size_t n_sum, size_t n, void* stream) {
+  if (!peers || world < 1 || world > GOF_MAX_PEERS || rank < 0 || rank >= world || (n & 3u) || (n_sum & 3u) || n_sum > n) {
+    gof_set_error("p2p_allreduce: bad arguments (world 1..8, n and n_sum multiples of 4, n_sum <= n)");
     return GOF_E_INVALID;
   }
   if (world == 1 || n == 0) return GOF_OK;
@@ -105,15 +169,13 @@ extern "C" GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world,
   const size_t begin = n4 * (size_t)rank / (size_t)world, end = n4 * (size_t)(rank + 1) / (size_t)world;
   if (end <= begin) return GOF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const size_t want = (end - begin + 511) / 512;
-  const unsigned grid = (unsigned)(want < (size_t)sms * 4 ? want : (size_t)sms * 4);
+  const unsigned grid = exchange_grid(end - begin);
+  const size_t sum_end = n_sum / 4;
   switch (world) {
-    case 2: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<2><<<grid, 512, 0, st>>>(a, begin, end)); break;
-    case 4: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<4><<<grid, 512, 0, st>>>(a, begin, end)); break;
-    case 8: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<8><<<grid, 512, 0, st>>>(a, begin, end)); break;
-    default: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce_any<<<grid, 512, 0, st>>>(a, world, begin, end)); break;
+    case 2: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<2><<<grid, 512, 0, st>>>(a, begin, end, sum_end)); break;
+    case 4: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<4><<<grid, 512, 0, st>>>(a, begin, end, sum_end)); break;
+    case 8: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce<8><<<grid, 512, 0, st>>>(a, begin, end, sum_end)); break;
+    default: GOF_LAUNCH("p2p_allreduce", st, k_p2p_allreduce_any<<<grid, 512, 0, st>>>(a, world, begin, end, sum_end)); break;
   }
   GOF_LAUNCH_CHECK(false, st);
   return GOF_OK;

@@ -236,6 +236,8 @@ struct PreBwdArgs {
   float* dL_dsh;
   float* dL_dscale;
   float* dL_drot;
+  float* dens_sum;          // optional [P][3]: |dL_dmean2D.xy|, |dL_dmean2D.z|, 1 for visible Gaussians (gof_rasterize_backward_stats)
+  float* dens_max;          // optional [P][2]: |dL_dmean2D.z|, radius
 };
 
 // m[c][r] column-major helpers mirroring the glm products used by backward.cu:381-587.  The chain rule through
@@ -293,6 +295,17 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
     // alpha = opacity * G, dL_dC = dL_dG * G * -1/2  =>  sum(G * dL_dalpha) = -2/opacity * sum(dL_dC)   (backward.cu:912)
     const float op = a.splat[idx].opacity;
     a.dL_dopacity[idx] = (accv[9] != 0.f) ? accv[9] * (-2.0f / op) : 0.f;
+    // this view's densification statistics (GaussianModel.add_densification_stats, scene/gaussian_model.py:709-714, and the
+    // max_radii2D update of train.py:255), written next to the gradients so that a view-parallel step reduces them in the
+    // same exchange instead of deriving them with a dozen elementwise kernels
+    if (a.dens_sum != nullptr) {
+      const float gz = fabsf(accv[15]);
+      a.dens_sum[3 * (size_t)idx + 0] = sqrtf(accv[13] * accv[13] + accv[14] * accv[14]);
+      a.dens_sum[3 * (size_t)idx + 1] = gz;
+      a.dens_sum[3 * (size_t)idx + 2] = 1.0f;
+      a.dens_max[2 * (size_t)idx + 0] = gz;
+      a.dens_max[2 * (size_t)idx + 1] = (float)a.radii[idx];
+    }
   }
 
   const float mx = a.means3D[3 * idx], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
@@ -566,7 +579,7 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
 int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const char* geom,
                                    const GofGeomLayout& L, const int* radii, float* dL_dmean2D, float* dL_dopacity,
                                    float* dL_dcolor, float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
-                                   float* dL_drot, cudaStream_t st) {
+                                   float* dL_drot, float* dens_sum, float* dens_max, cudaStream_t st) {
   (void)v;
   PreBwdArgs a;
   a.P = s->P; a.D = s->D; a.M = s->M;
@@ -578,6 +591,7 @@ int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const
   a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity;
   a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g; a.dL_dmean3D = dL_dmean3D; a.dL_dsh = dL_dsh;
   a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+  a.dens_sum = (dens_sum && dens_max) ? dens_sum : nullptr; a.dens_max = a.dens_sum ? dens_max : nullptr;
   GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + K8_THREADS - 1) / K8_THREADS, K8_THREADS, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;

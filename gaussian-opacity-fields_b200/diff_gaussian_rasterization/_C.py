@@ -53,6 +53,8 @@ _lib.gof_rasterize_forward.argtypes = [
     _fp, _fp, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
 _lib.gof_rasterize_backward.restype = ctypes.c_int
 _lib.gof_rasterize_backward.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int] + [_fp] * 15 + [ctypes.c_void_p]
+_lib.gof_rasterize_backward_stats.restype = ctypes.c_int
+_lib.gof_rasterize_backward_stats.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int] + [_fp] * 17 + [ctypes.c_void_p]
 _lib.gof_mark_visible.restype = ctypes.c_int
 _lib.gof_mark_visible.argtypes = [ctypes.c_int, _fp, _fp, _fp, _fp, ctypes.c_void_p]
 _lib.gof_integrate.restype = ctypes.c_int
@@ -285,12 +287,21 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         g = dL_dout_color.contiguous()
         rad = radii.contiguous()
         with torch.cuda.device(means3D.device):
-            _check(_lib.gof_rasterize_backward(
+            # `_out` may carry "dens_sum" (P,3) / "dens_max" (P,2): this view's densification statistics (gof_dp.GradBucket)
+            ds = _out.get("dens_sum") if _out is not None else None
+            dm = _out.get("dens_max") if _out is not None else None
+            if (ds is None) != (dm is None):
+                raise RuntimeError("gof_b200: _out needs both dens_sum and dens_max, or neither")
+            if ds is not None and not (ds.is_contiguous() and dm.is_contiguous() and tuple(ds.shape) == (P, 3) and tuple(dm.shape) == (P, 2)
+                                       and ds.dtype == torch.float32 and dm.dtype == torch.float32):
+                raise RuntimeError("gof_b200: dens_sum must be a contiguous float32 (P,3) and dens_max (P,2) tensor")
+            _check(_lib.gof_rasterize_backward_stats(
                 ctypes.byref(s), int(R), _ptr(rad, torch.int32), _ptr(geomBuffer, torch.uint8),
                 _ptr(binningBuffer, torch.uint8), _ptr(imageBuffer, torch.uint8), _ptr(g),
                 dL_dmeans2D.data_ptr(), None, dL_dopacity.data_ptr(), dL_dcolors.data_ptr(),
                 dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), _ptr(dL_dsh), dL_dscales.data_ptr(),
-                dL_drotations.data_ptr(), dL_dv2g.data_ptr(), _stream()))
+                dL_drotations.data_ptr(), dL_dv2g.data_ptr(), ds.data_ptr() if ds is not None else None,
+                dm.data_ptr() if dm is not None else None, _stream()))
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
             dL_dv2g)
 

@@ -6,9 +6,17 @@ so this module is new, not a port.  It uses torch.distributed (NCCL on GPUs, glo
 rasterizer backward writes its outputs directly into views of the flat buffer (`_out=` of
 `_C.rasterize_gaussians_backward`), so there is no pack/copy step before the collective.
 
-Exchange step: `GradBucket.all_reduce()` is NCCL's all-reduce.  `GradBucket.enable_peer_exchange()` switches it to the
-library's own kernel over NVLink peer memory (csrc/exchange.cu: every rank maps every rank's bucket through CUDA IPC,
-reduces its 1/N slice from all of them in rank order and stores it into all of them), bracketed by two NCCL barriers.
+Exchange step: `GradBucket.all_reduce()` is NCCL's all-reduce (SUM over the gradients and the summed statistics, MAX over
+the statistics' MAX tail).  `GradBucket.enable_peer_exchange()` switches it to the library's own kernel over NVLink peer
+memory (csrc/exchange.cu: every rank maps every rank's bucket through CUDA IPC, reduces its 1/N slice from all of them in rank
+order and stores it into all of them), bracketed by two NCCL barriers.  `GradBucket.enable_nvls_exchange()` moves the bucket
+into a torch symmetric-memory allocation (plumbing: it binds every rank's copy to one NVSwitch multicast object) and reduces
+it with the library's multimem kernel: the switch adds the ranks' copies (multimem.ld_reduce) and broadcasts the result
+(multimem.st) -- one bucket of NVLink traffic per GPU and direction instead of 2 (N-1)/N.
+
+The bucket also carries this view's densification statistics (written by the rasterizer backward itself, see
+gof_rasterize_backward_stats): `dens_sum` (P,3) = (|dL_dmean2D.xy|, |dL_dmean2D.z|, visible) reduced with SUM and `dens_max`
+(P,2) = (|dL_dmean2D.z|, radius) reduced with MAX -- what GaussianModel.add_densification_stats and train.py:255 accumulate.
 """
 import ctypes
 
@@ -17,16 +25,23 @@ import torch.distributed as dist
 
 # per-Gaussian parameter gradients that must be reduced across views: 3 + 48 + 1 + 3 + 4 = 59 floats
 _FIELDS = (("dmeans3D", (3,)), ("dsh", None), ("dopacity", (1,)), ("dscales", (3,)), ("drot", (4,)))
+_STAT_FIELDS = (("dens_sum", (3,)), ("dens_max", (2,)))       # SUM region ends where dens_max starts
 
 
 class GradBucket:
     """Flat fp32 buffer [sum of fields] with one contiguous, correctly shaped view per gradient tensor."""
 
-    def __init__(self, P, M, device, dtype=torch.float32):
+    def __init__(self, P, M, device, dtype=torch.float32, with_stats=True, extra_sum=0):
+        """`extra_sum`: additional floats summed with the gradients (view "extra": e.g. the appearance network's gradients)."""
         self.P, self.M = int(P), int(M)
         shapes = {}
         for name, tail in _FIELDS:
             shapes[name] = (self.P, self.M, 3) if name == "dsh" else (self.P,) + tail
+        if extra_sum:
+            shapes["extra"] = (int(extra_sum),)
+        if with_stats:
+            for name, tail in _STAT_FIELDS:
+                shapes[name] = (self.P,) + tail
         # Every field starts on a 256-byte boundary: k_preprocess_backward stores dL_drot as float4 and dL_dsh as
         # 128-bit rows, so the views must be 16-byte aligned for ANY P (after densification P is arbitrary).
         self._offsets, off = {}, 0
@@ -34,8 +49,10 @@ class GradBucket:
             self._offsets[name] = (off, shape)
             off += (int(torch.Size(shape).numel()) + 63) // 64 * 64
         self.numel = off
+        self.n_sum = self._offsets["dens_max"][0] if with_stats else off      # floats [0, n_sum): SUM, [n_sum, numel): MAX
         self.flat = torch.zeros(max(self.numel, 64), dtype=dtype, device=device)
         self.views = self._make_views()
+        self._symm = None        # torch symmetric-memory handle (NVLS exchange)
 
         self._peer_ptrs = None   # addresses (this process) of every rank's bucket, index = rank; own cudaMalloc at [rank]
         self._own_ptr, self._mapped = None, []
@@ -61,11 +78,11 @@ class GradBucket:
         if world > 8:
             raise RuntimeError("peer exchange: at most 8 ranks (one NVSwitch domain)")
         lib, dev, n = _C._lib, self.flat.device, self.flat.numel()
-        for f in ("gof_peer_alloc", "gof_peer_open", "gof_p2p_allreduce_sum_f32"):
+        for f in ("gof_peer_alloc", "gof_peer_open", "gof_p2p_allreduce_f32"):
             getattr(lib, f).restype = ctypes.c_int
         lib.gof_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]
         lib.gof_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
-        lib.gof_p2p_allreduce_sum_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        lib.gof_p2p_allreduce_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
         def agree(ok):   # True only if every rank says so: all ranks leave this function the same way (raise or return)
             t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float32, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
@@ -119,7 +136,7 @@ class GradBucket:
         self.flat.fill_(1.0)
         self.all_reduce(group=group)
         torch.cuda.synchronize(dev)
-        good = agree(bool((self.flat == float(world)).all().item()))
+        good = agree(bool((self.flat[:self.n_sum] == float(world)).all().item()) and bool((self.flat[self.n_sum:] == 1.0).all().item()))
         self.flat.zero_()
         if not good:
             self.close()
@@ -144,6 +161,15 @@ class GradBucket:
         """Leaves peer-exchange mode: unmaps the peers' buckets, frees the shared allocation and falls back to a torch-owned
         buffer + NCCL.  Collective when peer exchange was enabled (every rank must stop using its peers' memory first).
         The views are re-created (their contents are not kept)."""
+        if self.exchange == "nvls":
+            dev, n = self.flat.device, self.flat.numel()
+            if dist.is_available() and dist.is_initialized():
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=group)
+            self.exchange, self._symm = "nccl", None
+            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.views = self._make_views()
+            return
         if self.exchange != "p2p" and not self._own_ptr:
             return
         dev = self.flat.device
@@ -165,24 +191,88 @@ class GradBucket:
         except Exception:   # noqa: BLE001
             pass
 
+    def enable_nvls_exchange(self, group=None):
+        """Move the bucket into a torch symmetric-memory allocation -- every rank's copy bound to ONE NVSwitch multicast object
+        -- and switch all_reduce() to the library's multimem kernel (csrc/exchange.cu: k_nvls_allreduce).  Collective; the views
+        are re-created.  Raises (on every rank alike) when the fabric / driver offers no multicast or the self-test fails."""
+        from diff_gaussian_rasterization import _C
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self
+        if not self.flat.is_cuda or self.flat.dtype != torch.float32:
+            raise RuntimeError("NVLS exchange needs a CUDA float32 bucket")
+        import torch.distributed._symmetric_memory as symm_mem
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev, n = self.flat.device, self.flat.numel()
+        lib = _C._lib
+        lib.gof_nvls_allreduce_f32.restype = ctypes.c_int
+        lib.gof_nvls_allreduce_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
+
+        def agree(ok):
+            t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return float(t.item()) == 1.0
+
+        err, buf, hdl = None, None, None
+        try:
+            with torch.cuda.device(dev):
+                buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            if not int(hdl.multicast_ptr):
+                raise RuntimeError("this fabric / driver offers no multicast (multicast_ptr == 0)")
+        except Exception as e:   # noqa: BLE001 -- reported below, on every rank alike
+            err = e
+        if not agree(err is None):
+            raise RuntimeError(f"NVLS exchange: symmetric-memory setup failed on some rank ({err if err is not None else 'another rank'})")
+        old = (self.flat, self.views, self.exchange)
+        self.flat = buf
+        self.flat.zero_()
+        self.views = self._make_views()
+        self._symm, self._mc = hdl, int(hdl.multicast_ptr) + (buf.data_ptr() - int(hdl.buffer_ptrs[rank]))
+        self._sync = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lib, self._check, self._world, self._rank = lib, _C._check, world, rank
+        self.exchange = "nvls"
+        dist.barrier(group=group)
+        # self-test on the live mapping: rank r contributes r+1 to the SUM part and r to the MAX tail
+        self.flat[:self.n_sum].fill_(float(rank + 1))
+        self.flat[self.n_sum:].fill_(float(rank))
+        self.all_reduce(group=group)
+        torch.cuda.synchronize(dev)
+        good = bool((self.flat[:self.n_sum] == float(world * (world + 1) // 2)).all().item()) and \
+            bool((self.flat[self.n_sum:] == float(world - 1)).all().item())
+        good = agree(good)
+        self.flat.zero_()
+        if not good:
+            self.flat, self.views, self.exchange = old
+            self._symm = None
+            raise RuntimeError("NVLS exchange self-test failed on some rank")
+        return self
+
     def all_reduce(self, group=None, async_op=False):
-        """Sum over ranks.  World size 1: no-op."""
+        """SUM over ranks of floats [0, n_sum), MAX of the statistics tail [n_sum, numel).  World size 1: no-op."""
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
-        if self.exchange == "p2p":
+        if self.exchange in ("p2p", "nvls"):
             if async_op:
-                raise ValueError("GradBucket.all_reduce(async_op=True) is not available with the peer-memory exchange: "
+                raise ValueError("GradBucket.all_reduce(async_op=True) is not available with the peer-memory / NVLS exchange: "
                                  "the kernel is ordered on the current stream")
             # barrier: every rank's backward has filled its bucket (a 4-byte NCCL all-reduce on the same stream orders it
             # after the local kernels and completes only when every rank has reached it)
             dist.all_reduce(self._sync, group=group)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             with torch.cuda.device(self.flat.device):
-                self._check(self._lib.gof_p2p_allreduce_sum_f32(self._peer_ptrs, self._world, self._rank, self.flat.numel(),
-                                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                if self.exchange == "p2p":
+                    self._check(self._lib.gof_p2p_allreduce_f32(self._peer_ptrs, self._world, self._rank, self.n_sum, self.flat.numel(), stream))
+                else:
+                    self._check(self._lib.gof_nvls_allreduce_f32(ctypes.c_void_p(self._mc), self._world, self._rank, self.n_sum,
+                                                                 self.flat.numel(), stream))
             # barrier: every slice has been written into every bucket
             dist.all_reduce(self._sync, group=group)
             return None
-        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if self.n_sum == self.flat.numel():
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        w1 = dist.all_reduce(self.flat[:self.n_sum], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        w2 = dist.all_reduce(self.flat[self.n_sum:], op=dist.ReduceOp.MAX, group=group, async_op=async_op)
+        return (w1, w2) if async_op else None
 
     @property
     def nbytes(self):

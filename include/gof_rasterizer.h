@@ -102,6 +102,17 @@ GOF_API int gof_rasterize_backward(const gof_scene_t* scene, int num_rendered, c
                            float* dL_dview2gaussian,    /* [P,10] */
                            void* stream);
 
+/* gof_rasterize_backward that also leaves this view's densification statistics next to the gradients (view-parallel training
+ * reduces them in the same exchange): dens_sum [P,3] = (|dL_dmean2D.xy|, |dL_dmean2D.z|, 1) and dens_max [P,2] =
+ * (|dL_dmean2D.z|, radius) for visible Gaussians -- what GaussianModel.add_densification_stats (scene/gaussian_model.py:709-714)
+ * and train.py:255 accumulate per view with SUM resp. MAX.  Rows of invisible Gaussians are left untouched (pre-zero them).
+ * Both NULL: plain gof_rasterize_backward. */
+GOF_API int gof_rasterize_backward_stats(const gof_scene_t* scene, int num_rendered, const int* radii, void* geom_buffer,
+                           const void* binning_buffer, const void* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+                           float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                           float* dL_dsh, float* dL_dscale, float* dL_drot, float* dL_dview2gaussian, float* dens_sum,
+                           float* dens_max, void* stream);
+
 /* Rasterizer::integrate (rasterizer_impl.cu:530-792) == _C.integrate_gaussians_to_points.
  * out_alpha_integrated [PN] must be initialised to 1 and out_color_integrated [PN,3] to 0 by the
  * caller (rasterize_points.cu:277-278); out_color / radii zero-initialised. */
@@ -194,6 +205,14 @@ GOF_API int gof_stats_read(unsigned long long* out);
  * rank reduces its 1/world slice from all buffers (rank order 0..world-1: bit-identical results everywhere) and
  * stores it into all of them.  The caller brackets the call with two cross-rank barriers on `stream`. */
 GOF_API int gof_p2p_allreduce_sum_f32(float* const* peers, int world, int rank, size_t n, void* stream);
+/* The same with a MAX tail: floats [0, n_sum) are summed over the ranks, [n_sum, n) max-reduced (the densification statistics
+ * max_radii2D / xyz_gradient_accum_abs_max travel in the same bucket); n_sum, n multiples of 4. */
+GOF_API int gof_p2p_allreduce_f32(float* const* peers, int world, int rank, size_t n_sum, size_t n, void* stream);
+/* The same exchange reduced INSIDE the NVSwitch (NVLS): `mc` is the multicast address, valid in this process, of a buffer that
+ * every rank has bound to one multicast object at the same offset (e.g. a torch symmetric-memory allocation).  One kernel:
+ * multimem.ld_reduce of this rank's 1/world slice (sum, or unsigned max for the non-negative MAX tail) + multimem.st of the
+ * result to all ranks.  The caller brackets the call with two cross-rank barriers on `stream`. */
+GOF_API int gof_nvls_allreduce_f32(float* mc, int world, int rank, size_t n_sum, size_t n, void* stream);
 /* Enables peer access from the current device to `peer_device` (needed once per peer before kernels of this device
  * may dereference that peer's IPC-mapped memory).  Idempotent. */
 GOF_API int gof_enable_peer_access(int peer_device);

@@ -25,7 +25,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     P, M = 257, 16
     b = gof_dp.GradBucket(P, M, "cpu")
-    assert sum(v.numel() for v in b.views.values()) == P * 59
+    assert sum(v.numel() for v in b.views.values()) == P * (59 + 5)      # gradients + (dens_sum 3 | dens_max 2)
     g = torch.Generator().manual_seed(rank)
     local = {}
     for name, v in b.views.items():
@@ -56,9 +56,9 @@ def test_bucket_and_stats_allreduce_world2():
     res = [(r[0], {k: torch.from_numpy(v) for k, v in r[1].items()}, {k: torch.from_numpy(v) for k, v in r[2].items()},
             torch.from_numpy(r[3]), torch.from_numpy(r[4]), torch.from_numpy(r[5]), r[6]) for r in res]
     for name in res[0][1]:
-        total = res[0][1][name] + res[1][1][name]
+        total = torch.maximum(res[0][1][name], res[1][1][name]) if name == "dens_max" else res[0][1][name] + res[1][1][name]
         for r in range(world):
-            assert torch.equal(res[r][2][name], total), name
+            assert torch.equal(res[r][2][name], total), name     # dens_max rides in the MAX tail of the same bucket
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gaussian-opacity-fields_b200"))
     import gof_dp
@@ -78,6 +78,7 @@ def test_bucket_single_process_noop():
     b.views["dsh"].fill_(1.0)
     assert b.all_reduce() is None
     assert float(b.flat.sum()) == 10 * 48
+    assert gof_dp.GradBucket(10, 16, "cpu", with_stats=False).n_sum == gof_dp.GradBucket(10, 16, "cpu", with_stats=False).numel
     b.zero_()
     assert float(b.flat.abs().sum()) == 0.0
 
@@ -90,7 +91,8 @@ def test_bucket_layout_and_padding():
         b = gof_dp.GradBucket(P, 16, "cpu")
         assert b.flat.numel() % 64 == 0 and b.flat.numel() == b.numel
         last = -1
-        for name, per in (("dmeans3D", 3), ("dsh", 48), ("dopacity", 1), ("dscales", 3), ("drot", 4)):
+        assert b.n_sum == (b.views["dens_max"].data_ptr() - b.flat.data_ptr()) // 4      # SUM region ends where the MAX tail starts
+        for name, per in (("dmeans3D", 3), ("dsh", 48), ("dopacity", 1), ("dscales", 3), ("drot", 4), ("dens_sum", 3), ("dens_max", 2)):
             v = b.views[name]
             off = (v.data_ptr() - b.flat.data_ptr()) // 4
             assert v.numel() == per * P and v.is_contiguous()
