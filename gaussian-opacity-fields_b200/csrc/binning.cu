@@ -111,31 +111,33 @@ __device__ __forceinline__ uint32_t lookback_warp(uint32_t* status, uint32_t chu
   return excl;
 }
 
-// The same for the radix passes, where 256 digits look back at once: the status words of one digit are CONTIGUOUS over the
-// chunks ([digit][chunk] layout), so one 128-bit volatile load fetches four predecessors.  With all chunks of a pass resident
-// at the same time a chunk has to walk back over about half of its predecessors before it meets an inclusive prefix; four at a
-// time quarters the number of dependent L2 round trips that walk costs.
+// The same for the radix passes, where 256 digits look back at once: one 128-bit volatile load fetches the status words of four
+// consecutive predecessors.  With all chunks of a pass resident at the same time a chunk has to walk back over about half of
+// its predecessors before it meets an inclusive prefix; four at a time quarters the number of dependent L2 round trips.
 __device__ __forceinline__ uint4 ld_volatile_v4(const uint32_t* p) {
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ uint32_t lookback_row(uint32_t* row /* this digit's status words, 16-byte aligned */, uint32_t chunk,
-                                                 uint32_t aggregate) {
-  if (chunk == 0) {
-    st_volatile(row, LB_INC | aggregate);
-    return 0u;
-  }
-  st_volatile(row + chunk, LB_AGG | aggregate);
+// Status words of the radix passes: word (chunk c, digit d) lives at ((c >> 2) * 256 + d) * 4 + (c & 3) -- the four chunks of
+// a group are the four lanes of ONE 128-bit word per digit, and the 256 digits of a group are contiguous, so the 32 threads of
+// a warp (32 digits) poll 512 contiguous bytes per round trip.
+__device__ __forceinline__ void lookback_digit_publish(uint32_t* status, uint32_t digit, uint32_t chunk, uint32_t aggregate) {
+  st_volatile(status + ((size_t)(chunk >> 2) * GOF_RADIX + digit) * 4 + (chunk & 3u), (chunk == 0 ? LB_INC : LB_AGG) | aggregate);
+}
+__device__ __forceinline__ uint32_t lookback_digit_walk(uint32_t* status, uint32_t digit, uint32_t chunk, uint32_t aggregate) {
+  uint32_t* own = status + ((size_t)(chunk >> 2) * GOF_RADIX + digit) * 4 + (chunk & 3u);
+  if (chunk == 0) return 0u;
   uint32_t excl = 0u;
-  uint32_t pos = chunk;   // entries [0, pos) are still to be examined, from the top
+  uint32_t pos = chunk;   // chunks [0, pos) are still to be examined, from the top
   while (pos > 0) {
-    const uint32_t g0 = (pos - 1u) & ~3u;
-    const uint32_t need = pos - g0;   // entries g0 .. g0+need-1 of this group
+    const uint32_t g = (pos - 1u) >> 2;
+    const uint32_t need = pos - 4u * g;   // lanes 0 .. need-1 of this group
+    const uint32_t* word = status + ((size_t)g * GOF_RADIX + digit) * 4;
     uint4 w;
     bool ready;
     do {
-      w = ld_volatile_v4(row + g0);
+      w = ld_volatile_v4(word);
       ready = (w.x >> 30) != 0u && (need < 2u || (w.y >> 30) != 0u) && (need < 3u || (w.z >> 30) != 0u) && (need < 4u || (w.w >> 30) != 0u);
     } while (!ready);
     const uint32_t e[4] = {w.x, w.y, w.z, w.w};
@@ -148,9 +150,9 @@ __device__ __forceinline__ uint32_t lookback_row(uint32_t* row /* this digit's s
       }
     }
     if (done) break;
-    pos = g0;
+    pos = 4u * g;
   }
-  st_volatile(row + chunk, LB_INC | (excl + aggregate));
+  st_volatile(own, LB_INC | (excl + aggregate));
   return excl;
 }
 
@@ -185,7 +187,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(THREADS, 3) k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                         KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                                                         int shift, uint32_t mask, const uint32_t* __restrict__ ghist,
-                                                        uint32_t* __restrict__ status /* [256][stride] */, uint32_t stride,
+                                                        uint32_t* __restrict__ status /* see lookback_digit */,
                                                         uint32_t* __restrict__ ticket) {
   __shared__ uint32_t s_cnt[WARPS][GOF_RADIX];   // per-warp digit counters -> exclusive offsets over the warps
   __shared__ uint32_t s_gbase[GOF_RADIX];        // global position of this chunk's first key of each digit
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_onesweep(const KeyT* __restrict_
       s_cnt[w][threadIdx.x] = count;
       count += c;
     }
+    lookback_digit_publish(status, threadIdx.x, chunk, count);   // successors can start adding this chunk's counts at once
   }
   uint32_t chunk_n;
   const uint32_t lstart = block_excl_scan(count, &chunk_n);   // barrier inside
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_onesweep(const KeyT* __restrict_
     }
   }
   // the look-back (dependent L2 round trips) overlaps the value loads above
-  if (threadIdx.x <= mask) s_gbase[threadIdx.x] = gstart + lookback_row(status + (size_t)threadIdx.x * stride, chunk, count);
+  if (threadIdx.x <= mask) s_gbase[threadIdx.x] = gstart + lookback_digit_walk(status, threadIdx.x, chunk, count);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
@@ -274,8 +277,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_onesweep(const KeyT* __restrict_
 struct SortScratch {
   uint32_t* ghist;     // [4][256]
   uint32_t* tickets;   // [64]: [0..3] chunk tickets of the passes
-  uint32_t* status;    // [4][256][stride]: look-back status words, one row per digit
-  uint32_t stride;     // chunks rounded up to a multiple of 4, + 4
+  uint32_t* status;    // [4][chunk groups][256][4]: look-back status words (lookback_digit)
   size_t pass_words;   // words per pass in status
 };
 SortScratch carve_sort_scratch(uint32_t* scratch, size_t n) {
@@ -283,8 +285,7 @@ SortScratch carve_sort_scratch(uint32_t* scratch, size_t n) {
   s.ghist = scratch;
   s.tickets = scratch + 4 * GOF_RADIX;
   s.status = scratch + GOF_SORT_HEAD_BYTES / 4;
-  s.stride = (uint32_t)((gof_sort_blocks(n) + 3) / 4 * 4 + 4);
-  s.pass_words = (size_t)s.stride * GOF_RADIX;
+  s.pass_words = (size_t)((gof_sort_blocks(n) + 3) / 4 + 1) * GOF_RADIX * 4;
   return s;
 }
 
@@ -308,7 +309,7 @@ int onesweep_passes(KeyT* ka, KeyT* kb, uint32_t* va, uint32_t* vb, size_t n, co
     const bool a2b = (p % 2 == 0);
     GOF_LAUNCH("radix_onesweep", st, k_onesweep<KeyT><<<nb, THREADS, 0, st>>>(
         a2b ? ka : kb, a2b ? va : vb, a2b ? kb : ka, a2b ? vb : va, n, dg.shift[p], dg.mask[p], sc.ghist + p * GOF_RADIX,
-        sc.status + (size_t)p * sc.pass_words, sc.stride, sc.tickets + p));
+        sc.status + (size_t)p * sc.pass_words, sc.tickets + p));
     GOF_LAUNCH_CHECK(debug, st);
   }
   return GOF_OK;
@@ -443,14 +444,14 @@ __global__ void __launch_bounds__(THREADS) k_scan_emit(int P, const uint32_t* __
 
 // rasterizer_impl.cu:149-171 identifyTileRanges on the sorted tile ids (ranges pre-zeroed, :365)
 template <typename KeyT>
-__global__ void __launch_bounds__(256) k_tile_ranges(size_t L, const KeyT* __restrict__ keys, uint2* __restrict__ ranges) {
+__global__ void __launch_bounds__(256) k_tile_ranges(size_t L, const KeyT* __restrict__ keys, uint2* __restrict__ ranges, int key_shift) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= L) return;
-  const uint32_t cur = (uint32_t)keys[idx];
+  const uint32_t cur = (uint32_t)keys[idx] >> key_shift;   // tile id = key >> key_shift (the query points' keys carry the pixel below it)
   if (idx == 0)
     ranges[cur].x = 0;
   else {
-    const uint32_t prev = (uint32_t)keys[idx - 1];
+    const uint32_t prev = (uint32_t)keys[idx - 1] >> key_shift;
     if (cur != prev) {
       ranges[prev].y = (uint32_t)idx;
       ranges[cur].x = (uint32_t)idx;
@@ -492,7 +493,7 @@ int bin_tiles_t(int P, size_t R, const GofView& v, char* geom, const GofGeomLayo
   const int rc = onesweep_passes<KeyT>(ka, kb, va, vb, R, dg, sc, debug, st);
   if (rc != GOF_OK) return rc;
   const KeyT* sorted = reinterpret_cast<const KeyT*>(bin + BL.sorted_keys);
-  GOF_LAUNCH("tile_ranges", st, k_tile_ranges<KeyT><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, sorted, ranges));
+  GOF_LAUNCH("tile_ranges", st, k_tile_ranges<KeyT><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, sorted, ranges, 0));
   GOF_LAUNCH_CHECK(debug, st);
   return GOF_OK;
 }
@@ -509,19 +510,22 @@ int gof_depth_sort_and_offsets(int P, char* geom, const GofGeomLayout& L, bool d
                               reinterpret_cast<uint32_t*>(geom + L.hist), (size_t)P, 32, debug, st, &in_b);
 }
 
-// Stable sort of `n` (tile id, index) pairs by tile id (ids < 2^nbits) for the integrate path's query points, then
-// the per-tile ranges of the first ids < num_tiles (ranges must hold num_tiles + 1 uint2; the last slot absorbs the
+// Stable sort of `n` (key, index) pairs on the low nbits of the key for the integrate path's query points (tile id = key >>
+// key_shift; the bits below it order the points of a tile by pixel), then the per-tile ranges of the first ids < num_tiles (ranges must hold num_tiles + 1 uint2; the last slot absorbs the
 // sentinel id given to points outside the image).  Buffers: keys/vals ping-pong (u32), scratch as in gof_sort_scratch_bytes.
-int gof_sort_points_by_tile(size_t n, int nbits, uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist,
+int gof_sort_points_by_tile(size_t n, int nbits, int key_shift, uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist,
                             uint2* ranges, int num_tiles, bool debug, cudaStream_t st, int* result_in_b) {
-  if (gof_binning_legacy()) return legacy_gof_sort_points_by_tile(n, nbits, ka, kb, va, vb, hist, ranges, num_tiles, debug, st, result_in_b);
+  if (gof_binning_legacy()) {
+    if (key_shift != 0) { gof_set_error("legacy binning sorts plain tile ids"); return GOF_E_INVALID; }
+    return legacy_gof_sort_points_by_tile(n, nbits, ka, kb, va, vb, hist, ranges, num_tiles, debug, st, result_in_b);
+  }
   GOF_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)(num_tiles + 1) * sizeof(uint2), st));
   *result_in_b = 0;
   if (n == 0) return GOF_OK;
   const int rc = sort_pairs<uint32_t>(ka, kb, va, vb, hist, n, nbits, debug, st, result_in_b);
   if (rc != GOF_OK) return rc;
   const uint32_t* sorted = *result_in_b ? kb : ka;
-  GOF_LAUNCH("tile_ranges", st, k_tile_ranges<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, sorted, ranges));
+  GOF_LAUNCH("tile_ranges", st, k_tile_ranges<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, sorted, ranges, key_shift));
   GOF_LAUNCH_CHECK(debug, st);
   return GOF_OK;
 }

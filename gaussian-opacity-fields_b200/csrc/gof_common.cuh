@@ -324,7 +324,8 @@ int gof_depth_sort_and_offsets(int P, char* geom, const GofGeomLayout& L, bool d
 int gof_bin_tiles(int P, size_t R, const GofView& v, char* geom, const GofGeomLayout& GL, char* bin,
                   const GofBinLayout& BL, char* img, const GofImageLayout& IL, bool debug, cudaStream_t st);
 
-int gof_sort_points_by_tile(size_t n, int nbits, uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist,
+bool gof_binning_legacy();
+int gof_sort_points_by_tile(size_t n, int nbits, int key_shift, uint32_t* ka, uint32_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist,
                             uint2* ranges, int num_tiles, bool debug, cudaStream_t st, int* result_in_b);
 
 // integrate.cu

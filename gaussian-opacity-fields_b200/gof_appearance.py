@@ -1,0 +1,100 @@
+"""Decoupled appearance (BASELINE config 4): the reference's AppearanceNetwork
+(scene/appearance_network.py:18-46) and L1_loss_appearance (train.py:67-88) -- callers of the rasterizer, the only
+GEMM-shaped math on the path.
+
+Same module structure and parameter names as the reference (conv1, up1.conv ... up4.conv, conv2, conv3), so a reference
+checkpoint's `appearance_network` state_dict loads unchanged.  The convolutions run through torch (cuDNN; TF32 tensor-core math
+is the reference's own default, torch.backends.cudnn.allow_tf32): at 1080p the network costs ~16 GFLOP forward, dominated by
+the 16->16 convolution at full resolution, and is kept on the library path -- DESIGN.md states its measured share of a C4 step.
+What this module adds over the reference's formulation: the per-view tensors the loss re-creates every iteration (crop window,
+the embedding broadcast to the 1/32 grid) are built without the `repeat().permute()` copy, and `appearance_grads_flat` /
+`load_flat_grads_` pack the network's and the embedding's gradients into the view-parallel gradient bucket
+(gof_dp.GradBucket(extra_sum=...)) so that they travel in the same exchange as the Gaussian gradients."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class UpsampleBlock(nn.Module):   # scene/appearance_network.py:5-16
+    def __init__(self, num_input_channels, num_output_channels):
+        super().__init__()
+        self.pixel_shuffle = nn.PixelShuffle(2)
+        self.conv = nn.Conv2d(num_input_channels // 4, num_output_channels, 3, stride=1, padding=1)
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        return self.relu(self.conv(self.pixel_shuffle(x)))
+
+
+class AppearanceNetwork(nn.Module):   # scene/appearance_network.py:18-46
+    def __init__(self, num_input_channels, num_output_channels):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_input_channels, 256, 3, stride=1, padding=1)
+        self.up1 = UpsampleBlock(256, 128)
+        self.up2 = UpsampleBlock(128, 64)
+        self.up3 = UpsampleBlock(64, 32)
+        self.up4 = UpsampleBlock(32, 16)
+        self.conv2 = nn.Conv2d(16, 16, 3, stride=1, padding=1)
+        self.conv3 = nn.Conv2d(16, num_output_channels, 3, stride=1, padding=1)
+        self.relu = nn.ReLU()
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, x):
+        x = self.relu(self.conv1(x))
+        x = self.up4(self.up3(self.up2(self.up1(x))))
+        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        x = self.relu(self.conv2(x))
+        return self.sigmoid(self.conv3(x))
+
+
+def crop_window(origH, origW):
+    """train.py:70-75: the centred crop to multiples of 32."""
+    H, W = origH // 32 * 32, origW // 32 * 32
+    left, top = origW // 2 - W // 2, origH // 2 - H // 2
+    return top, left, H, W
+
+
+def l1_loss_appearance(image, gt_image, network, appearance_embedding, return_transformed_image=False):
+    """L1_loss_appearance (train.py:67-88) with the model pieces passed explicitly: `appearance_embedding` is the view's row
+    of GaussianModel._appearance_embeddings (64 floats), `network` the AppearanceNetwork."""
+    origH, origW = image.shape[1:]
+    top, left, H, W = crop_window(origH, origW)
+    crop_image = image[:, top:top + H, left:left + W]
+    crop_gt_image = gt_image[:, top:top + H, left:left + W]
+    crop_image_down = F.interpolate(crop_image[None], size=(H // 32, W // 32), mode="bilinear", align_corners=True)[0]
+    emb = appearance_embedding.reshape(-1, 1, 1).expand(-1, H // 32, W // 32)      # the reference: repeat(H/32, W/32, 1).permute(2, 0, 1)
+    mapping_image = network(torch.cat([crop_image_down, emb], dim=0)[None])
+    transformed_image = mapping_image * crop_image
+    if not return_transformed_image:
+        return torch.abs(transformed_image - crop_gt_image).mean()            # utils/loss_utils.py:17-18 l1_loss
+    return F.interpolate(transformed_image, size=(origH, origW), mode="bilinear", align_corners=True)[0]
+
+
+def appearance_numel(network, n_embedding=64):
+    return sum(p.numel() for p in network.parameters()) + int(n_embedding)
+
+
+def appearance_grads_flat(network, embedding_grad, out):
+    """Packs d loss / d (network parameters, this view's embedding row) into the flat tensor `out` (the `extra` view of a
+    gof_dp.GradBucket) in parameter order followed by the embedding row."""
+    off = 0
+    for p in network.parameters():
+        n = p.numel()
+        if p.grad is not None:
+            out[off:off + n].copy_(p.grad.reshape(-1))
+        else:
+            out[off:off + n].zero_()
+        off += n
+    out[off:off + embedding_grad.numel()].copy_(embedding_grad.reshape(-1))
+    return out
+
+
+def load_flat_grads_(network, flat):
+    """Inverse of appearance_grads_flat for the network part: writes the exchanged sums back into .grad; returns the
+    embedding-row gradient slice."""
+    off = 0
+    for p in network.parameters():
+        n = p.numel()
+        p.grad = flat[off:off + n].view_as(p).clone()
+        off += n
+    return flat[off:]
