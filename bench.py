@@ -194,7 +194,7 @@ E2E_API = ("GaussianRasterizer.forward + autograd backward + L1/normal/depth/dis
            "slot one step late -- the SAME harness (bench.run_e2e_harness) drives both arms")
 
 
-def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls):
+def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls, app=None):
     """End-to-end steps through a package's public drop-in API (`GaussianRasterizer(settings)(...)` + autograd), used
     unchanged for this repo's package and for the reference's own package (--impl reference), so that the two `e2e`
     numbers differ only in the rasterizer.  Input pipeline as a training loop runs it: this step's camera + ground-truth
@@ -237,11 +237,17 @@ def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls):
             p.grad = None
         img, radii = rasterizer_cls(rs)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
                                         shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
-        loss = (img[:3] - gt_buf[b]).abs().mean() + 0.05 * (img[3:6] ** 2).mean() + 0.01 * img[6].mean() + 100.0 * img[8].mean()
+        l_rgb = app.loss(img[:3], gt_buf[b], wl.view(step)) if app is not None else (img[:3] - gt_buf[b]).abs().mean()
+        loss = l_rgb + 0.05 * (img[3:6] ** 2).mean() + 0.01 * img[6].mean() + 100.0 * img[8].mean()
+        if app is not None:
+            for p in app.params:
+                p.grad = None
+            app.emb.grad = None
         loss.backward()
         consumed[b].record(main)
         if world > 1:
-            flat = torch.cat([params[k].grad.flatten() for k in ("means3D", "shs", "opacities", "scales", "rotations")])
+            flat = torch.cat([params[k].grad.flatten() for k in ("means3D", "shs", "opacities", "scales", "rotations")] +
+                             ([p.grad.flatten() for p in app.params] + [app.emb.grad[wl.view(step)]] if app is not None else []))
             dist.all_reduce(flat)
         loss_done[b ^ 1].synchronize()                                # D2H of the PREVIOUS step's loss has landed
         losses.append(float(loss_pin[b ^ 1][0]))
@@ -267,13 +273,72 @@ def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls):
     return e2e_ms, h2d
 
 
+APPEARANCE_NOTE = "; decoupled appearance on (AppearanceNetwork(67,3) + 64-float view embedding, L1_loss_appearance on the rgb channels)"
+
+
+def metric_name(wl):
+    m = "training views/sec (fwd+bwd) @1080p, %s Gaussians" % ("1M" if wl.P == 1_000_000 else f"{wl.P / 1e6:g}M")
+    return m + (", decoupled appearance" if wl.cfg.get("appearance") else "")
+
+
+class AppearanceStep:
+    """Config C4: the appearance part of a training step (train.py:157-159) for either arm -- `which` = "ours" uses
+    gof_appearance, "reference" the reference's own AppearanceNetwork class and L1_loss_appearance text (staged, tests/_refpy)."""
+
+    def __init__(self, wl, dev, which):
+        import types
+        torch.manual_seed(7)
+        if which == "ours":
+            import gof_appearance
+            self.net = gof_appearance.AppearanceNetwork(67, 3).to(dev)
+            self.loss = lambda img, gt, idx: gof_appearance.l1_loss_appearance(img, gt, self.net, self.emb[idx])
+        else:
+            import importlib.util
+            import _refpy
+            spec = importlib.util.spec_from_file_location("gof_ref_appearance_network", _refpy.staged("scene", "appearance_network.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            self.net = mod.AppearanceNetwork(67, 3).to(dev)
+            fn = _refpy.ref_function("train.py", "L1_loss_appearance", {"torch": torch, "l1_loss": _refpy.ref_utils("loss_utils").l1_loss})
+            stub = types.SimpleNamespace(get_apperance_embedding=lambda idx: self.emb[idx], appearance_network=self.net)
+            self.loss = lambda img, gt, idx: fn(img, gt, stub, idx)
+        self.emb = (torch.randn(2048, 64, device=dev) * 1e-4).requires_grad_(True)          # scene/gaussian_model.py:113-116
+        self.params = list(self.net.parameters())
+        self.numel = sum(p.numel() for p in self.params) + 64
+        self.gt = wl.gt_host.to(dev)
+        self.dL_rest = wl.dL[3:].contiguous()
+        self.ev = []
+
+    def loss_grad(self, color, view, extra_out):
+        """d loss / d render (9,H,W) for this view; packs the network / embedding-row gradients into `extra_out` (flat)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rgb = color[:3].detach().requires_grad_(True)
+        loss = self.loss(rgb, self.gt, view)
+        grads = torch.autograd.grad(loss, [rgb, self.emb] + self.params)
+        off = 0
+        for g in grads[2:]:
+            extra_out[off:off + g.numel()].copy_(g.reshape(-1)); off += g.numel()
+        extra_out[off:off + 64].copy_(grads[1][view])
+        dL = torch.cat([grads[0], self.dL_rest], dim=0)
+        e1.record()
+        self.ev.append((e0, e1))
+        return dL
+
+    def timed_ms(self):
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in self.ev[-20:]]
+        return sum(ts) / max(len(ts), 1)
+
+
 # --------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, dev):
     from diff_gaussian_rasterization import _C, GaussianRasterizer, GaussianRasterizationSettings
     import gof_dp
 
     wl = Workload(args.config, dev, rank, world)
-    bucket = gof_dp.GradBucket(wl.P, 16, dev)
+    app = AppearanceStep(wl, dev, "ours") if wl.cfg.get("appearance") else None
+    bucket = gof_dp.GradBucket(wl.P, 16, dev, extra_sum=app.numel if app else 0)
     exchange_note = None
     if world > 1 and args.exchange != "nccl":
         # every enable_* call is collective and fails on all ranks alike (it ends with an agreement all-reduce and a self-test
@@ -294,7 +359,10 @@ def run_ours(args, rank, world, dev):
         fa = wl.fwd_args(v)
         R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
         bucket.zero_()
-        grads = _C.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, wl.dL), _out=bucket.views)
+        # config C4 (decoupled appearance, train.py:157-159): d loss / d rgb comes from the appearance loss of this view, the
+        # network's and the embedding row's gradients join the Gaussian gradients in the bucket
+        dL = app.loss_grad(color, v, bucket.views["extra"]) if app else wl.dL
+        grads = _C.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, dL), _out=bucket.views)
         if world > 1:
             bucket.all_reduce()      # gradients (SUM) and this step's densification statistics (SUM | MAX tail) in ONE exchange
         return color
@@ -366,7 +434,7 @@ def run_ours(args, rank, world, dev):
     del geom_s, bin_s, img_s
 
     # ---- end to end through the public API with host inputs (the same harness times the reference arm) --------
-    e2e_ms, h2d = run_e2e_harness(args, wl, world, dev, GaussianRasterizer, GaussianRasterizationSettings)
+    e2e_ms, h2d = run_e2e_harness(args, wl, world, dev, GaussianRasterizer, GaussianRasterizationSettings, app)
 
     # the exchange step alone (N > 1): one all-reduce of the 59-float/Gaussian gradient bucket, CUDA events, max over ranks
     allreduce_ms = None
@@ -395,10 +463,10 @@ def run_ours(args, rank, world, dev):
     achieved = (dom_bytes / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9) if dom_ms > 0 else None
 
     line = {
-        "metric": "training views/sec (fwd+bwd) @1080p, 1M Gaussians", "value": world * args.steps / (ms * 1e-3),
+        "metric": metric_name(wl), "value": world * args.steps / (ms * 1e-3),
         "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_FMT.format(cfg=args.config, P=wl.P, W=wl.W, H=wl.H, seed=wl.cfg["seed"]),
+        "config": {"workload": WORKLOAD_FMT.format(cfg=args.config, P=wl.P, W=wl.W, H=wl.H, seed=wl.cfg["seed"]) + (APPEARANCE_NOTE if app else ""),
                    "visible": V, "num_rendered": R, "stats_view": stats_view, **tile_stats,
                    "parallelism": f"view-parallel dp{world}" if world > 1 else "single GPU",
                    "l2": "no explicit flush: a step touches >400 MB (> 126 MB L2) and every step renders a new view"},
@@ -416,6 +484,10 @@ def run_ours(args, rank, world, dev):
                      "step_frac": step_bytes / ((ms / args.steps) * 1e-3) / 1e9 / peak},
         "kernels_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
+    if app:
+        line["appearance"] = {"ms_per_step": app.timed_ms(), "params": app.numel,
+                              "what": "AppearanceNetwork(67,3) forward + backward on the 1056x1920 crop and L1 (gof_appearance, torch/cuDNN convolutions, "
+                                      "TF32 like the reference's default), CUDA events, inside the step"}
     if allreduce_ms is not None:
         what = {"p2p": "59 gradient + 5 statistics f32 per Gaussian by the library's kernel over NVLink peer memory (csrc/exchange.cu), two NCCL barriers",
                 "nvls": "59 gradient + 5 statistics f32 per Gaussian reduced inside the NVSwitch by the library's multimem kernel "
@@ -534,13 +606,17 @@ def run_reference(args, rank, world, dev):
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     wl = Workload(args.config, dev, rank, world)
     st = {}
+    app = AppearanceStep(wl, dev, "reference") if wl.cfg.get("appearance") else None
+    app_flat = torch.zeros(app.numel, device=dev) if app else None
 
     def step_device(step):
-        fa = wl.fwd_args(wl.view(step))
+        v = wl.view(step)
+        fa = wl.fwd_args(v)
         R, color, radii, geom, binning, img = ref.rasterize_gaussians(*fa)
-        grads = ref.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, wl.dL))
+        dL = app.loss_grad(color, v, app_flat) if app else wl.dL
+        grads = ref.rasterize_gaussians_backward(*bwd_args(fa, radii, geom, R, binning, img, dL))
         if world > 1:
-            flat = torch.cat([grads[i].flatten() for i in (3, 5, 2, 6, 7)])
+            flat = torch.cat([grads[i].flatten() for i in (3, 5, 2, 6, 7)] + ([app_flat] if app else []))
             dist.all_reduce(flat)
 
     for s in range(args.warmup):
@@ -565,16 +641,16 @@ def run_reference(args, rank, world, dev):
     if pkg is None:   # staged Python missing: same call structure over the extension's entry points
         pkg = _reference_api_shim(ref)
         api_note = "reference extension entry points behind a minimal autograd shim (staged reference Python absent)"
-    e2e_ms, h2d = run_e2e_harness(args, wl, world, dev, pkg.GaussianRasterizer, pkg.GaussianRasterizationSettings)
+    e2e_ms, h2d = run_e2e_harness(args, wl, world, dev, pkg.GaussianRasterizer, pkg.GaussianRasterizationSettings, app)
     stats_view = wl.view(args.warmup)
     o = ref.rasterize_gaussians(*wl.fwd_args(stats_view))
     st["R"], st["radii"] = o[0], o[2]
     del o
     return {
-        "metric": "training views/sec (fwd+bwd) @1080p, 1M Gaussians", "impl": "reference", "value": world * args.steps / (ms * 1e-3),
+        "metric": metric_name(wl), "impl": "reference", "value": world * args.steps / (ms * 1e-3),
         "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_FMT.format(cfg=args.config, P=wl.P, W=wl.W, H=wl.H, seed=wl.cfg["seed"]),
+        "config": {"workload": WORKLOAD_FMT.format(cfg=args.config, P=wl.P, W=wl.W, H=wl.H, seed=wl.cfg["seed"]) + (APPEARANCE_NOTE if app else ""),
                    "visible": int((st["radii"] > 0).sum()), "num_rendered": int(st["R"]), "stats_view": stats_view,
                    "reference": "unmodified diff-gaussian-rasterization of GOF compiled for sm_100a (oracle/build_ref.sh), on the GPU"},
         "cpu_baseline": {"kind": "reference", "cores": 0, "value": world * args.steps / (ms * 1e-3), "unit": "views/s",
@@ -874,6 +950,150 @@ def run_extract_reference(args, rank, world, dev):
     }
 
 
+# ==============================================================================================================
+# --mode train_step: one whole training iteration around the rasterizer (SURVEY 8(f) ranks 1-2 next to the hot path)
+# ==============================================================================================================
+TRAIN_METRIC = "training iterations/sec (activations + render + loss + backward + Adam) @1080p"
+_LRS = {"_xyz": 1.6e-4, "_features_dc": 2.5e-3, "_features_rest": 2.5e-3 / 20, "_opacity": 0.05, "_scaling": 0.005, "_rotation": 0.001}
+_LAMBDAS = (0.2, 0.05, 100.0)      # lambda_dssim, lambda_depth_normal, lambda_distortion (arguments/__init__.py)
+
+
+def _raw_params(wl, dev):
+    g = wl.gs
+    return {"_xyz": g["means3D"].clone(), "_scaling": torch.log(g["scales"]), "_rotation": g["rotations"].clone(),
+            "_opacity": torch.logit(g["opacities"].clamp(1e-4, 1 - 1e-4)), "_features_dc": g["shs"][:, :1].contiguous(),
+            "_features_rest": g["shs"][:, 1:].contiguous()}
+
+
+def run_train_step(args, rank, world, dev):
+    """ours:       gof_params.activate -> GaussianRasterizer -> gof_loss.view_loss -> backward -> [all-reduce] -> gof_params.adam_step
+    reference:  torch activations (scene/gaussian_model.py:152-194) -> the reference's rasterizer package -> the reference's own
+                l1_loss / ssim / depth_to_normal as train.py:151-188 combines them -> backward -> [all-reduce] -> torch.optim.Adam(eps=1e-15)
+    Host inputs per step (camera + ground-truth image) come from pinned memory, the loss is read back: every step is end to end."""
+    import types
+    import torch.nn.functional as F
+    ours = args.impl == "ours"
+    wl = Workload(args.config, dev, rank, world)
+    filt = (torch.rand(wl.P, 1, generator=torch.Generator().manual_seed(5)) * 0.002).to(dev)
+    raw = {k: v.to(dev).requires_grad_(True) for k, v in _raw_params(wl, dev).items()}
+    cam_buf = torch.empty(35, device=dev)
+    gt_buf = torch.empty(3, wl.H, wl.W, device=dev)
+    loss_pin = torch.zeros(1).pin_memory()
+    if ours:
+        import gof_loss
+        import gof_params
+        from diff_gaussian_rasterization import GaussianRasterizer, GaussianRasterizationSettings
+        state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in raw.items()}
+    else:
+        import _refpy
+        pkg = _refpy.ref_rasterizer_package()
+        lu, du = _refpy.ref_utils("loss_utils"), _refpy.ref_utils("depth_utils")
+        if pkg is None or lu is None or du is None:
+            return {"impl": "reference", "unavailable": "reference extension / staged Python not built here (needs /root/reference at build time)"}
+        GaussianRasterizer, GaussianRasterizationSettings = pkg.GaussianRasterizer, pkg.GaussianRasterizationSettings
+        opt = torch.optim.Adam([{"params": [v], "lr": _LRS[k]} for k, v in raw.items()], lr=0.0, eps=1e-15)
+    it = [0]
+
+    def step(s):
+        it[0] += 1
+        v = wl.view(s)
+        c = wl.cams[v]
+        cam_buf.copy_(wl.cam_host[v], non_blocking=True)
+        gt_buf.copy_(wl.gt_host, non_blocking=True)
+        wvt = cam_buf[:16].view(4, 4)
+        rs = GaussianRasterizationSettings(image_height=wl.H, image_width=wl.W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, kernel_size=0.0,
+                                           subpixel_offset=wl.subpix, bg=wl.bg, scale_modifier=1.0, viewmatrix=wvt,
+                                           projmatrix=cam_buf[16:32].view(4, 4), sh_degree=3, campos=cam_buf[32:35], prefiltered=False, debug=False)
+        means2D = torch.zeros_like(raw["_xyz"], requires_grad=True)
+        if ours:
+            for p in raw.values():
+                p.grad = None
+            scales, rots, ops, shs = gof_params.activate(raw["_scaling"], raw["_rotation"], raw["_opacity"], filt, raw["_features_dc"], raw["_features_rest"])
+        else:
+            opt.zero_grad(set_to_none=True)
+            sc = torch.exp(raw["_scaling"])                                   # get_scaling_with_3D_filter, :157-163
+            s2 = torch.square(sc)
+            scales = torch.sqrt(s2 + torch.square(filt))
+            coef = torch.sqrt(s2.prod(dim=1) / (s2 + torch.square(filt)).prod(dim=1))      # get_opacity_with_3D_filter, :173-185
+            ops = torch.sigmoid(raw["_opacity"]) * coef[..., None]
+            rots = F.normalize(raw["_rotation"])                              # get_rotation, :165-167
+            shs = torch.cat((raw["_features_dc"], raw["_features_rest"]), dim=1)   # get_features, :187-191
+        img, radii = GaussianRasterizer(rs)(means3D=raw["_xyz"], means2D=means2D, opacities=ops, shs=shs, scales=scales, rotations=rots)
+        if ours:
+            loss, _terms = gof_loss.view_loss(img, gt_buf, c.world_view_transform, c.tanfovx, c.tanfovy, *_LAMBDAS, rotation=wl.rot9[v])
+        else:
+            view = types.SimpleNamespace(world_view_transform=wvt, image_width=wl.W, image_height=wl.H, FoVx=2 * math.atan(c.tanfovx),
+                                         FoVy=2 * math.atan(c.tanfovy))
+            image = img[:3]
+            rgb_loss = (1.0 - _LAMBDAS[0]) * lu.l1_loss(image, gt_buf) + _LAMBDAS[0] * (1.0 - lu.ssim(image, gt_buf))      # train.py:156-161
+            depth_normal, _ = du.depth_to_normal(view, img[6][None])                                                         # :170-186
+            depth_normal = depth_normal.permute(2, 0, 1)
+            render_normal = F.normalize(img[3:6], p=2, dim=0)
+            c2w = (wvt.T).inverse()
+            rnw = (c2w[:3, :3] @ render_normal.reshape(3, -1)).reshape(3, *render_normal.shape[1:])
+            loss = rgb_loss + (1 - (rnw * depth_normal).sum(dim=0)).mean() * _LAMBDAS[1] + img[8].mean() * _LAMBDAS[2]
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.flatten() for p in raw.values()])
+            dist.all_reduce(flat)
+            off = 0
+            for p in raw.values():
+                p.grad = flat[off:off + p.numel()].view_as(p); off += p.numel()
+        if ours:
+            with torch.no_grad():
+                for k, p in raw.items():
+                    gof_params.adam_step(p.data, state[k][0], state[k][1], p.grad.contiguous(), _LRS[k], it[0])
+        else:
+            opt.step()
+        loss_pin.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss_pin
+
+    if ours:
+        import gof_loss as _gl
+        wl.rot9 = [_gl.camera_rotation(c.world_view_transform) for c in wl.cams]
+    for s in range(args.warmup):
+        step(s)
+    barrier_sync(world)
+    launches0 = 0
+    if ours:
+        from diff_gaussian_rasterization import _C
+        launches0 = _C.launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    e1.record()
+    barrier_sync(world)
+    wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    final = float(loss_pin[0])
+    assert math.isfinite(final)
+    h2d = 35 * 4 + wl.gt_host.numel() * 4
+    line = {"metric": TRAIN_METRIC, "value": world * args.steps / (ms * 1e-3), "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "mode": "train_step",
+            "config": {"workload": WORKLOAD_FMT.format(cfg=args.config, P=wl.P, W=wl.W, H=wl.H, seed=wl.cfg["seed"]),
+                       "iteration": ("gof_params.activate -> GaussianRasterizer -> gof_loss.view_loss -> backward -> gof_params.adam_step" if ours else
+                                     "torch activations -> reference rasterizer package -> reference l1_loss/ssim/depth_to_normal (train.py:151-188) "
+                                     "-> backward -> torch.optim.Adam(eps=1e-15)"),
+                       "final_loss": final},
+            "e2e": {"value": world * args.steps / (wall_ms * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": wall_ms / args.steps, "api": "the same loop on the host clock: camera + ground-truth image from pinned memory and the loss read back every step"},
+            "clocks": clocks}
+    if not ours:
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"kind": "reference", "cores": 0, "value": line["value"], "unit": "iterations/s",
+                                "sample": "the reference has no CPU path; this arm runs its own CUDA kernels + torch on the same B200"}
+    else:
+        line["gpu_launches"] = int(_C.launch_count() - launches0)
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -882,6 +1102,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(gof_synth.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="raster", choices=["raster", "train_step"],
+                    help="raster (default): the rasterizer fwd+bwd step of BASELINE.json; train_step: a whole training iteration around it")
     ap.add_argument("--points", type=int, default=0, help="C5: number of query points (default: the config's 50 M)")
     ap.add_argument("--views", type=int, default=0, help="C5: number of views on the ring (default 64)")
     ap.add_argument("--tets", type=int, default=0, help="C5: number of tetrahedra of the pipeline run (default 6.5 per point)")
@@ -903,7 +1125,9 @@ def main():
     extract = "points" in gof_synth.CONFIGS[args.config]
     if extract and args.steps == 50:
         args.steps = 16          # a step is a 50 M-point query: keep the default run within minutes
-    if extract:
+    if args.mode == "train_step" and not extract:
+        line = run_train_step(args, rank, world, dev)
+    elif extract:
         line = run_extract_ours(args, rank, world, dev) if args.impl == "ours" else run_extract_reference(args, rank, world, dev)
     else:
         line = run_ours(args, rank, world, dev) if args.impl == "ours" else run_reference(args, rank, world, dev)

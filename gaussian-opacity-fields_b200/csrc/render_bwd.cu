@@ -9,8 +9,8 @@
 // re-evaluating t, G and alpha with the forward's operation sequence (gof_math.cuh) so that they are bit-identical.
 // The traversal starts at the last Gaussian any pixel of the tile blended.
 // Staging of the per-tile slab (64-byte record + 32-byte backward record per list entry) as in render_fwd.cu: bulk copies
-// completing on an mbarrier (default), cp.async, or the round-1 load/store staging (GOF_STAGE=bulk|cpasync|regs), double
-// buffered in 2 x 24 KB of dynamic shared memory so that batch i-1 lands while batch i is walked.
+// completing on an mbarrier, cp.async, or the round-1 load/store staging (GOF_STAGE_BWD=bulk|cpasync|regs; regs is the default
+// -- see the launcher for the measurements), the first two double buffered in 2 x 24 KB of dynamic shared memory.
 #include <stdlib.h>
 
 #include "gof_common.cuh"
@@ -361,7 +361,11 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geo
   if (stage < 0) {
     const char* e = getenv("GOF_STAGE_BWD");
     if (!e) e = getenv("GOF_STAGE");
-    stage = !e ? 1 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1));
+    // default: the round-1 staging.  Measured at the benchmark workload with right-sized carveouts (profiles/r2_ab_staging_call3.jsonl):
+    // regs 2.06 ms, cp.async 2.10 ms, bulk 2.14 ms -- the backward walks each batch once and four CTAs per SM already cover the
+    // gather latency, while the two per-thread bulk copies cost ~18 issue slots per record (ELECT loop) and the double buffer
+    // takes 96 KB of L1 away from the mask / spill traffic.  The forward gains 7 % from the same change and keeps it.
+    stage = !e ? 0 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1));
   }
   const size_t smem = (size_t)(stage ? 2 : 1) * BATCH * 96;
 #define GOF_BWD_LAUNCH(STATS, MINB, STG)                                                                                      \
