@@ -68,7 +68,32 @@ __device__ __forceinline__ float warp_reduce16(const float (&a)[16], int lane) {
 }
 
 // STAGE: 0 = registers + st.shared (round 1), 1 = cp.async.bulk + mbarrier, 2 = cp.async (LDGSTS)
-template <bool STATS, int MINB, int STAGE>
+// The same over a QUARTER of the warp -- the 8 lanes of a 4x2 pixel block: lanes that differ in bits 0, 1 (x) and 3 (y) only --
+// with 14 shuffles.  On return r0 / r1 hold the quarter-wide sums of values number `base` and `base + 1`,
+// base = (lane & 8 ? 8 : 0) + (lane & 2 ? 4 : 0) + (lane & 1 ? 2 : 0).
+__device__ __forceinline__ void quarter_reduce16(const float (&a)[16], int lane, float* r0, float* r1) {
+  float b[8], c[4];
+  const bool h3 = lane & 8, h1 = lane & 2, h0 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = h3 ? a[i] : a[i + 8], keep = h3 ? a[i + 8] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h1 ? b[i] : b[i + 4], keep = h1 ? b[i + 4] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const float send0 = h0 ? c[0] : c[2], keep0 = h0 ? c[2] : c[0];
+    const float send1 = h0 ? c[1] : c[3], keep1 = h0 ? c[3] : c[1];
+    *r0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 1);
+    *r1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);
+  }
+}
+
+// SUB: the four 4x2 pixel blocks of a warp walk their OWN lists (see the loop); otherwise the warp walks one list (round 1)
+template <bool STATS, int MINB, int STAGE, bool SUB>
 __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const BwdArgs a) {
   constexpr bool BULK = STAGE == 1, CPA = STAGE == 2;
   unsigned long long st_visit = 0, st_eval = 0, st_pass = 0, st_contrib = 0, st_anyhit = 0;
@@ -212,18 +237,11 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
       // the forward wrote the masks of every group up to this warp's deepest contributor; nothing behind it blended
       if ((uint32_t)gstart >= warp_last) continue;
       const uint32_t mybits = __ldg(vm_row + gstart);        // bit b: this pixel blended entry gstart+b
-      uint32_t m = __reduce_or_sync(0xffffffffu, mybits);
-      while (m) {
-        const int b = 31 - __clz(m);
-        m &= ~(1u << b);
-        const int j = k * 32 + b;
-        // zero-based index of this Gaussian in the tile list == the reference's `contributor` after its
-        // decrement (backward.cu:763)
-        const uint32_t contributor = (uint32_t)(gstart + b);
-        bool contrib = ((mybits >> b) & 1u) != 0u;   // implies inside && contributor < last_contributor
-        if (STATS) { st_visit += (lane == 0); st_eval += contrib; st_pass += contrib; }
 
-        const uint32_t row = buf_base + (uint32_t)j * 96u;
+      // the 16 partial gradients of ONE (pixel, Gaussian) pair: row = the staged record, contributor = its zero-based index in the
+      // tile list (the reference's `contributor` after its decrement, backward.cu:763), contrib = this pixel blended it
+      auto pair_grad = [&](const uint32_t row, const uint32_t contributor, const bool contrib, float (&g)[16]) {
+        if (STATS) { st_eval += contrib; st_pass += contrib; }
         const float4 q0 = gof_lds128<0>(row), q1 = gof_lds128<16>(row), q2 = gof_lds128<32>(row);
         const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
         GofPair p;
@@ -238,9 +256,7 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
           alpha = fminf(F_MUL(q2.z, G), GOF_ALPHA_MAX);
         }
         if (STATS) st_contrib += contrib;
-        if (STATS) st_anyhit += (lane == 0);
 
-        float g[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) g[q] = 0.f;
         if (contrib) {
@@ -320,11 +336,53 @@ __global__ void __launch_bounds__(GOF_BLOCK_SIZE, MINB) k_render_backward(const 
           g[7] = dB2 * ry;
           g[8] = dB2;
         }
-        const float sum = warp_reduce16(g, lane);
-        // one red per even lane into the Gaussian's 64-byte accumulator row: 16 global float atomics per (warp, Gaussian)
-        // instead of 17 per (pixel, Gaussian); dL_dopacity = -2/opacity * sum(dL_dC) is formed by k_preprocess_backward
-        const uint32_t gid = __float_as_uint(gof_lds32<84>(row));   // GofSplatBwd::self
-        if (!(lane & 1) && sum != 0.f) atomicAdd(a.grad_acc + ((size_t)gid * 16 + vidx), sum);
+      };
+
+      if (!SUB) {
+        uint32_t m = __reduce_or_sync(0xffffffffu, mybits);
+        while (m) {
+          const int b = 31 - __clz(m);
+          m &= ~(1u << b);
+          const uint32_t row = buf_base + (uint32_t)(k * 32 + b) * 96u;
+          const bool contrib = ((mybits >> b) & 1u) != 0u;   // implies inside && contributor < last_contributor
+          if (STATS) { st_visit += (lane == 0); st_anyhit += (lane == 0); }
+          float g[16];
+          pair_grad(row, (uint32_t)(gstart + b), contrib, g);
+          const float sum = warp_reduce16(g, lane);
+          // one red per even lane into the Gaussian's 64-byte accumulator row: 16 global float atomics per (warp, Gaussian)
+          // instead of 17 per (pixel, Gaussian); dL_dopacity = -2/opacity * sum(dL_dC) is formed by k_preprocess_backward
+          const uint32_t gid = __float_as_uint(gof_lds32<84>(row));   // GofSplatBwd::self
+          if (!(lane & 1) && sum != 0.f) atomicAdd(a.grad_acc + ((size_t)gid * 16 + vidx), sum);
+        }
+      } else {
+        // Each 4x2 pixel block (a quarter of the warp: the lanes that differ in bits 0, 1, 3) walks ITS OWN list -- the entries one
+        // of its 8 pixels blended -- in lockstep with the other three: an iteration handles up to four different Gaussians, one per
+        // quarter.  A Gaussian of pixel-scale footprint touches 16 of a warp's 32 pixels on average, so the warp-wide walk leaves
+        // half of the lanes idle; quarter-wide, 4.9 M instead of 5.9 M iterations cover the same 93 M pairs at the benchmark
+        // workload (profiles/r2_mask_stats_c3.json).  The partial gradients are reduced over the quarter (14 shuffles) and leave
+        // as two reds per lane.
+        uint32_t qb = mybits;
+        qb |= __shfl_xor_sync(0xffffffffu, qb, 1);
+        qb |= __shfl_xor_sync(0xffffffffu, qb, 2);
+        qb |= __shfl_xor_sync(0xffffffffu, qb, 8);
+        while (__any_sync(0xffffffffu, qb != 0u)) {
+          const bool act = qb != 0u;
+          const int b = act ? 31 - __clz(qb) : 0;
+          if (act) qb &= ~(1u << b);
+          const uint32_t row = buf_base + (uint32_t)(k * 32 + b) * 96u;
+          const bool contrib = act && ((mybits >> b) & 1u) != 0u;
+          if (STATS) { st_visit += (lane == 0); st_anyhit += act && !(lane & 11); }
+          float g[16];
+          pair_grad(row, (uint32_t)(gstart + b), contrib, g);
+          float r0, r1;
+          quarter_reduce16(g, lane, &r0, &r1);
+          if (act) {
+            const uint32_t gid = __float_as_uint(gof_lds32<84>(row));   // GofSplatBwd::self
+            float* dst = a.grad_acc + ((size_t)gid * 16 + ((lane & 8) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0));
+            if (r0 != 0.f) atomicAdd(dst, r0);
+            if (r1 != 0.f) atomicAdd(dst + 1, r1);
+          }
+        }
       }
     }
   }
@@ -367,23 +425,30 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geo
     // takes 96 KB of L1 away from the mask / spill traffic.  The forward gains 7 % from the same change and keeps it.
     stage = !e ? 0 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1));
   }
+  static int sub = -1;   // GOF_SUBWARP=0: one list per warp (round 1); default: one list per 4x2 pixel block
+  if (sub < 0) { const char* e = getenv("GOF_SUBWARP"); sub = (e && e[0] == '0') ? 0 : 1; }
   const size_t smem = (size_t)(stage ? 2 : 1) * BATCH * 96;
-#define GOF_BWD_LAUNCH(STATS, MINB, STG)                                                                                      \
+#define GOF_BWD_LAUNCH(STATS, MINB, STG, SUBW)                                                                                      \
   do {                                                                                                                        \
     static bool attr_set = false;                                                                                             \
     if (!attr_set) {                                                                                                          \
-      GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BATCH * 96)); \
+      GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG, SUBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BATCH * 96)); \
       const int need = MINB * ((STG ? 2 : 1) * BATCH * 96 + 1024 + 128);   /* only what MINB CTAs need: the rest stays L1 */             \
-      GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG>, cudaFuncAttributePreferredSharedMemoryCarveout,                \
+      GOF_CUDA_OK(cudaFuncSetAttribute(k_render_backward<STATS, MINB, STG, SUBW>, cudaFuncAttributePreferredSharedMemoryCarveout,                \
                                        (need * 100 + 233471) / 233472 > 100 ? 100 : (need * 100 + 233471) / 233472));                     \
       attr_set = true;                                                                                                        \
     }                                                                                                                         \
-    GOF_LAUNCH("render_bwd", st, k_render_backward<STATS, MINB, STG><<<v.tiles, GOF_BLOCK_SIZE, smem, st>>>(a));             \
+    GOF_LAUNCH("render_bwd", st, k_render_backward<STATS, MINB, STG, SUBW><<<v.tiles, GOF_BLOCK_SIZE, smem, st>>>(a));       \
   } while (0)
 #define GOF_BWD_STAGES(STATS, MINB)                                                                   \
   do {                                                                                                \
-    if (stage == 1) GOF_BWD_LAUNCH(STATS, MINB, 1); else if (stage == 2) GOF_BWD_LAUNCH(STATS, MINB, 2); \
-    else GOF_BWD_LAUNCH(STATS, MINB, 0);                                                              \
+    if (sub) {                                                                                         \
+      if (stage == 1) GOF_BWD_LAUNCH(STATS, MINB, 1, true); else if (stage == 2) GOF_BWD_LAUNCH(STATS, MINB, 2, true); \
+      else GOF_BWD_LAUNCH(STATS, MINB, 0, true);                                                       \
+    } else {                                                                                           \
+      if (stage == 1) GOF_BWD_LAUNCH(STATS, MINB, 1, false); else if (stage == 2) GOF_BWD_LAUNCH(STATS, MINB, 2, false); \
+      else GOF_BWD_LAUNCH(STATS, MINB, 0, false);                                                      \
+    }                                                                                                  \
   } while (0)
   if (a.stats) GOF_BWD_STAGES(true, 3);
   else if (occ >= 4) GOF_BWD_STAGES(false, 4);

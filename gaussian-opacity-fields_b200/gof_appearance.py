@@ -40,6 +40,11 @@ class AppearanceNetwork(nn.Module):   # scene/appearance_network.py:18-46
         self.sigmoid = nn.Sigmoid()
 
     def forward(self, x):
+        if x.is_cuda:
+            # NHWC activations: with 8..16 channels at full resolution cuDNN's NCHW kernels run far from the tensor cores; the
+            # channels-last ones (TF32, like the reference's default math) are its fast path.  Parameters may stay as they are
+            # (cuDNN transforms the 3x3 filters on the fly); results agree to TF32 rounding either way.
+            x = x.contiguous(memory_format=torch.channels_last)
         x = self.relu(self.conv1(x))
         x = self.up4(self.up3(self.up2(self.up1(x))))
         x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)

@@ -61,21 +61,29 @@ def make_camera(width, height, view=0, n_views=64, radius=4.0, fovx_deg=60.0, el
 
 
 def make_gaussians(P, seed, focal_x, sh_degree=3, sigma_px=2.0, sigma_spread=0.7, extent=1.5, radius=4.0):
-    """P random Gaussians: dict of CPU float32 tensors shaped like GaussianModel's activated properties."""
+    """P random Gaussians: dict of CPU float32 tensors shaped like GaussianModel's activated properties.
+
+    Everything is drawn and transformed in float64 and rounded to float32 ONCE at the end.  Round 1 generated in float32, and
+    torch's vectorised CPU exp / sigmoid / normal sampling differ by an ulp between hosts (AVX2 vs AVX-512 code paths of
+    SLEEF): one Gaussian's footprint then touched one tile more or less and `num_rendered` of the same workload differed by one
+    between the bench box and the scaling box.  A float64 ulp survives the final rounding only when the value sits within
+    2^-29 of a float32 rounding boundary, so the float32 scene is the same on every host."""
     g = torch.Generator().manual_seed(int(seed))
-    means3D = (torch.rand(P, 3, generator=g) * 2.0 - 1.0) * extent
-    sig = torch.exp(math.log(sigma_px) + sigma_spread * torch.randn(P, 1, generator=g))
-    aniso = torch.exp(torch.rand(P, 3, generator=g) * math.log(1.0 / 0.3) + math.log(0.3))
+    f64 = torch.float64
+    means3D = (torch.rand(P, 3, generator=g, dtype=f64) * 2.0 - 1.0) * extent
+    sig = torch.exp(math.log(sigma_px) + sigma_spread * torch.randn(P, 1, generator=g, dtype=f64))
+    aniso = torch.exp(torch.rand(P, 3, generator=g, dtype=f64) * math.log(1.0 / 0.3) + math.log(0.3))
     scales = (sig * radius / focal_x) * aniso
-    rot = torch.randn(P, 4, generator=g)
+    rot = torch.randn(P, 4, generator=g, dtype=f64)
     rotations = rot / rot.norm(dim=1, keepdim=True)
-    opacities = torch.sigmoid(1.5 * torch.randn(P, 1, generator=g))
+    opacities = torch.sigmoid(1.5 * torch.randn(P, 1, generator=g, dtype=f64))
     M = 16
-    shs = torch.zeros(P, M, 3)
-    shs[:, 0, :] = (torch.rand(P, 3, generator=g) * 2.0 - 1.0) * 1.77
-    shs[:, 1:, :] = 0.1 * torch.randn(P, M - 1, 3, generator=g)
-    return {"means3D": means3D.contiguous(), "scales": scales.contiguous(), "rotations": rotations.contiguous(),
-            "opacities": opacities.contiguous(), "shs": shs.contiguous(), "sh_degree": sh_degree}
+    shs = torch.zeros(P, M, 3, dtype=f64)
+    shs[:, 0, :] = (torch.rand(P, 3, generator=g, dtype=f64) * 2.0 - 1.0) * 1.77
+    shs[:, 1:, :] = 0.1 * torch.randn(P, M - 1, 3, generator=g, dtype=f64)
+    f32 = lambda t: t.to(torch.float32).contiguous()   # noqa: E731
+    return {"means3D": f32(means3D), "scales": f32(scales), "rotations": f32(rotations), "opacities": f32(opacities), "shs": f32(shs),
+            "sh_degree": sh_degree}
 
 
 # the configurations of BASELINE.json / BASELINE.md section 2.2
