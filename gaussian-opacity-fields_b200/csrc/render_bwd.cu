@@ -425,8 +425,9 @@ int gof_launch_render_backward(const gof_scene_t* s, const GofView& v, char* geo
     // takes 96 KB of L1 away from the mask / spill traffic.  The forward gains 7 % from the same change and keeps it.
     stage = !e ? 0 : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 2 : 1));
   }
-  static int sub = -1;   // GOF_SUBWARP=0: one list per warp (round 1); default: one list per 4x2 pixel block
-  if (sub < 0) { const char* e = getenv("GOF_SUBWARP"); sub = (e && e[0] == '0') ? 0 : 1; }
+  // GOF_SUBWARP_BWD=0: one list per warp (round 1); default: one list per 4x2 pixel block (2.09 -> 1.86 ms, profiles/r2_ab_subwarp_call5.jsonl)
+  static int sub = -1;
+  if (sub < 0) { const char* e = getenv("GOF_SUBWARP_BWD"); sub = (e && e[0] == '0') ? 0 : 1; }
   const size_t smem = (size_t)(stage ? 2 : 1) * BATCH * 96;
 #define GOF_BWD_LAUNCH(STATS, MINB, STG, SUBW)                                                                                      \
   do {                                                                                                                        \

@@ -328,8 +328,12 @@ int gof_launch_render_forward(const gof_scene_t* s, const GofView& v, const char
     }                                                                                                                         \
     GOF_LAUNCH("render_fwd", st, k_render_forward<MINB, STG, SUBW><<<v.tiles, GOF_BLOCK_SIZE, 0, st>>>(a));                  \
   } while (0)
-  static int sub = -1;   // GOF_SUBWARP=0: one list per warp (round 1); default: one list per 4x2 pixel block
-  if (sub < 0) { const char* e = getenv("GOF_SUBWARP"); sub = (e && e[0] == '0') ? 0 : 1; }
+  // GOF_SUBWARP_FWD=1: one list per 4x2 pixel block.  Off by default: measured 1.50 ms against 1.29 ms for the warp-wide walk at the
+  // benchmark workload (profiles/r2_ab_subwarp_call5.jsonl) -- the forward's visit is short (44 % end in the 20-instruction reject),
+  // so four ballots per group, the per-lane loop control and 40 more bytes of spills cost more than the 11 % fewer iterations
+  // save.  The backward, whose visit is 320 instructions, gains 11 % from the same idea and uses it.
+  static int sub = -1;
+  if (sub < 0) { const char* e = getenv("GOF_SUBWARP_FWD"); sub = (e && e[0] == '1') ? 1 : 0; }
 #define GOF_FWD_STAGES(MINB, SUBW) \
   do { if (stage == 1) GOF_FWD_LAUNCH(MINB, 1, SUBW); else if (stage == 2) GOF_FWD_LAUNCH(MINB, 2, SUBW); else GOF_FWD_LAUNCH(MINB, 0, SUBW); } while (0)
   if (occ >= 4) { if (sub) GOF_FWD_STAGES(4, true); else GOF_FWD_STAGES(4, false); }

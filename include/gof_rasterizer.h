@@ -252,6 +252,21 @@ GOF_API int gof_activate_params_backward(int P, int M_rest, const float* scaling
  * T, focal_x, focal_y, width, height.  scratch4: 4 device bytes. */
 GOF_API int gof_compute_3d_filter(int P, const float* xyz, int n_cams, const float* cams, float max_focal, float* filter_3D,
                                   void* scratch4, void* stream);
+/* GaussianModel.densify_and_prune (scene/gaussian_model.py:631-707) in three steps (csrc/densify.cu):
+ * plan   -- the four keep-flags of every Gaussian (kept original | clone | split child 1 | split child 2) from the accumulated
+ *           statistics and their exclusive scans; flags / offsets [4][P] u32, totals [4] u32 on the device;
+ * emit   -- per output row (blocks in that order, ascending source index) its source Gaussian and kind, the re-sampled
+ *           positions and the raw scalings; totals_host = the four block sizes read back; noise = optional [3][P][3] standard
+ *           normal samples, otherwise Philox(seed);
+ * gather -- dst[o,:] = src[src_index[o],:] for one parameter / optimizer-state tensor (zero_new: rows of new Gaussians are 0). */
+GOF_API int gof_densify_plan(int P, const float* accum, const float* accum_abs, const float* denom, const float* scaling_raw,
+                             const float* opacity_raw, float max_grad, float abs_threshold, float dense_extent, float min_opacity,
+                             float prune_scale, uint32_t* flags, uint32_t* offsets, uint32_t* totals, uint32_t* scan_tmp, void* stream);
+GOF_API int gof_densify_emit(int P, const uint32_t* flags, const uint32_t* offsets, const uint32_t* totals_host, const float* xyz,
+                             const float* scaling_raw, const float* rotation_raw, const float* noise, unsigned long long seed,
+                             int32_t* src_index, unsigned char* kind, float* new_xyz, float* new_scaling_raw, void* stream);
+GOF_API int gof_gather_rows_f32(const float* src, int row_floats, const int32_t* src_index, const unsigned char* kind, size_t n_out,
+                                int zero_new, float* dst, void* stream);
 GOF_API int gof_adam_step(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, double lr, double beta1,
                           double beta2, double eps, int step, void* stream);
 

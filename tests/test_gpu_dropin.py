@@ -93,9 +93,10 @@ def test_reference_render_runs_on_this_package(renderers, pipe_name):
         assert _util.rel_err(po["render"][ch], pr["render"][ch])[0] < tol, f"channel {ch}"
     assert _util.rel_err(vo, vr1)[0] <= max(1e-4, 6 * _util.rel_err(vr2, vr1)[0])
     for k in go:
-        noise = _util.rel_err(gr2[k], gr1[k])[0]
-        err = _util.rel_err(go[k], gr1[k])[0]
-        assert err <= max(1e-4, 6.0 * noise), f"{pipe_name}/{k}: ours-vs-ref {err}, ref-vs-ref {noise}"
+        j = 1 if k in ("xyz", "scales", "rotation") else 0      # noise-amplified gradients: relative L2 (see test_gpu_live_ref._grad_close)
+        noise = _util.rel_err(gr2[k], gr1[k])[j]
+        err = _util.rel_err(go[k], gr1[k])[j]
+        assert err <= max(1e-4, (3.0 if j else 6.0) * noise), f"{pipe_name}/{k}: ours-vs-ref {err}, ref-vs-ref {noise}"
 
 
 def test_reference_integrate_runs_on_this_package(renderers):

@@ -12,6 +12,21 @@ pytestmark = pytest.mark.gpu
 NAMES = ["dmeans2D", "dcolors", "dopacity", "dmeans3D", "dcov3D", "dsh", "dscales", "drot", "dv2g"]
 
 
+AMPLIFIED = ("dmeans3D", "dscales", "drot")
+
+
+def _grad_close(n, ours, ref1, ref2):
+    """ours-vs-reference against the reference's own run-to-run noise.  The accumulated gradients are compared in max-norm.  For
+    dL_dmeans3D / dL_dscales / dL_drot the view2gaussian chain rule multiplies the atomics' summation noise by ~1/scale^2: their
+    max-norm difference between two REFERENCE runs is a heavy-tailed random number (0.17 ... 0.88 for dscales on the same C2
+    scene), so those are compared in relative L2 -- stable to a few percent between runs -- and pinned deterministically against
+    the fp64 oracle in test_gpu_grad_fp64.py."""
+    k = 1 if n in AMPLIFIED else 0
+    noise = _util.rel_err(ref2, ref1)[k]
+    err = _util.rel_err(ours, ref1)[k]
+    assert err <= max(1e-4, (3.0 if k else 6.0) * noise), f"{n}: ours-vs-ref {err}, ref-vs-ref {noise} ({'L2' if k else 'max-norm'})"
+
+
 @pytest.fixture(scope="module")
 def ref():
     m = _util.load_ref()
@@ -50,9 +65,7 @@ def test_full_size_against_live_reference(ref, name, view):
     g1 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
     g2 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
     for n, a, b, c in zip(NAMES, go, g1, g2):
-        noise = _util.rel_err(c, b)[0]
-        err = _util.rel_err(a, b)[0]
-        assert err <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {err}, ref-vs-ref {noise}"
+        _grad_close(n, a, b, c)
 
 
 @pytest.mark.parametrize("M,deg", [(4, 1), (9, 2), (16, 2)])
@@ -123,8 +136,7 @@ def test_view2gaussian_precomp_against_live_reference(ref):
     g1 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
     g2 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
     for n, a, b, c in zip(NAMES, go, g1, g2):
-        noise = _util.rel_err(c, b)[0]
-        assert _util.rel_err(a, b)[0] <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {_util.rel_err(a, b)[0]}, ref-vs-ref {noise}"
+        _grad_close(n, a, b, c)
 
 
 def _cov3d_from(scales, rotations, mod):
@@ -182,8 +194,7 @@ def test_cov3d_precomp_against_live_reference(ref, with_v2g):
     g1 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
     g2 = ref.rasterize_gaussians_backward(*_util.bwd_args(fa, radr, ger, Rr, binr, imr, grad))
     for n, a, b, c in zip(NAMES, go, g1, g2):
-        noise = _util.rel_err(c, b)[0]
-        assert _util.rel_err(a, b)[0] <= max(1e-4, 6.0 * noise), f"{n}: ours-vs-ref {_util.rel_err(a, b)[0]}, ref-vs-ref {noise}"
+        _grad_close(n, a, b, c)
     assert float(go[4].abs().max()) == 0.0          # dL_dcov3D stays zero (backward.cu:991-1007: EWA backward disabled)
 
 
