@@ -340,25 +340,22 @@ def run_ours(args, rank, world, dev):
     app = AppearanceStep(wl, dev, "ours") if wl.cfg.get("appearance") else None
     bucket = gof_dp.GradBucket(wl.P, 16, dev, extra_sum=app.numel if app else 0)
     exchange_note = None
-    if world > 1 and args.exchange != "nccl":
-        # every enable_* call is collective and fails on all ranks alike (it ends with an agreement all-reduce and a self-test
-        # on the live mapping), so the fallback chain below takes the same branch everywhere
-        order = {"auto": ("nvls", "p2p"), "nvls": ("nvls",), "p2p": ("p2p",)}[args.exchange]
-        notes = []
-        for mode in order:
-            try:
-                bucket.enable_nvls_exchange() if mode == "nvls" else bucket.enable_peer_exchange()
-                break
-            except Exception as e:   # noqa: BLE001 -- e.g. no multicast / no peer access on this box: say so and fall back
-                notes.append(f"{mode} unavailable ({type(e).__name__}: {str(e)[:160]})")
-        if notes:
-            exchange_note = "; ".join(notes) + (f"; using {bucket.exchange}" if bucket.exchange != "nccl" else "; NCCL all-reduce used")
+    exchange_tuning = None
+    if world > 1 and args.exchange == "auto":
+        # every mode is adopted only after a collective self-test on the live mapping, timed, and the fastest kept (same decision
+        # on every rank: the times are max-reduced)
+        exchange_tuning = bucket.autotune_exchange()
+    elif world > 1 and args.exchange != "nccl":
+        try:
+            bucket.enable_nvls_exchange() if args.exchange == "nvls" else bucket.enable_peer_exchange()
+        except Exception as e:   # noqa: BLE001 -- symmetric on all ranks: e.g. no multicast / no peer access on this box
+            exchange_note = f"{args.exchange} unavailable ({type(e).__name__}: {str(e)[:160]}); NCCL all-reduce used"
 
     def step_device(step):
         v = wl.view(step)
         fa = wl.fwd_args(v)
         R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
-        bucket.zero_()
+        # (no bucket.zero_(): the backward writes every element of its outputs, zeros included)
         # config C4 (decoupled appearance, train.py:157-159): d loss / d rgb comes from the appearance loss of this view, the
         # network's and the embedding row's gradients join the Gaussian gradients in the bucket
         dL = app.loss_grad(color, v, bucket.views["extra"]) if app else wl.dL
@@ -495,6 +492,8 @@ def run_ours(args, rank, world, dev):
                 "nccl": "all-reduce(SUM) of 59 gradient + 3 statistics f32 per Gaussian and all-reduce(MAX) of 2 (NCCL)"}[bucket.exchange]
         line["exchange"] = {"impl": bucket.exchange, "what": what, "bytes": int(bucket.nbytes), "ms": allreduce_ms}
         line["exchange_check"] = exchange_check
+        if exchange_tuning:
+            line["exchange"]["autotune_ms"] = exchange_tuning
         info = nccl_info()
         if info:
             line["exchange"]["nccl_info"] = info

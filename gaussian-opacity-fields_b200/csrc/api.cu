@@ -308,7 +308,7 @@ extern "C" int gof_rasterize_backward_stats(const gof_scene_t* s, int num_render
                                             float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                                             float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                                             float* dL_dview2gaussian, float* dens_sum, float* dens_max, void* stream) {
-  (void)dL_dconic; (void)dL_dcov3D;
+  (void)dL_dconic;
   int rc = validate_scene(s);
   if (rc != GOF_OK) return rc;
   if (s->P == 0) return GOF_OK;   // rasterize_points.cu:172
@@ -334,7 +334,7 @@ extern "C" int gof_rasterize_backward_stats(const gof_scene_t* s, int num_render
                                        st)) != GOF_OK)
     return rc;
   return gof_launch_preprocess_backward(s, v, geom, GL, radii, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dview2gaussian, dL_dmean3D,
-                                        dL_dsh, dL_dscale, dL_drot, dens_sum, dens_max, st);
+                                        dL_dsh, dL_dscale, dL_drot, dL_dcov3D, dens_sum, dens_max, st);
 }
 
 extern "C" int gof_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

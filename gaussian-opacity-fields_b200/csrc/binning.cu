@@ -43,8 +43,7 @@ namespace {
 
 constexpr int THREADS = GOF_BLOCK_SIZE;              // 256
 constexpr int WARPS = THREADS / 32;
-constexpr int ITEMS = GOF_SORT_ITEMS;                // 16 keys per thread
-constexpr int CHUNK = GOF_SORT_CHUNK;                // 4096 keys per CTA
+// keys per thread / per CTA of a one-sweep pass are template parameters (GOF_SORT_KEYS=8|16, default chosen by measurement)
 constexpr uint32_t LB_AGG = 1u << 30;                // status word = flag (2 bits) | count (30 bits): written and read as ONE word
 constexpr uint32_t LB_INC = 2u << 30;
 constexpr uint32_t LB_VAL = (1u << 30) - 1u;
@@ -183,7 +182,7 @@ __global__ void __launch_bounds__(THREADS) k_digit_hist(const KeyT* __restrict__
 // ------------------------------------------------------------------------------------------------
 // One stable LSD radix pass in one launch.  Chunk c = keys [c*4096, (c+1)*4096); warp w of the CTA owns a contiguous
 // 1/8 of it, 32 keys per round: (chunk, warp, round, lane) order == input order, ranks within a digit follow it.
-template <typename KeyT>
+template <typename KeyT, int ITEMS>
 __global__ void __launch_bounds__(THREADS, 3) k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                         KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                                                         int shift, uint32_t mask, const uint32_t* __restrict__ ghist,
@@ -192,6 +191,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_onesweep(const KeyT* __restrict_
   __shared__ uint32_t s_cnt[WARPS][GOF_RADIX];   // per-warp digit counters -> exclusive offsets over the warps
   __shared__ uint32_t s_gbase[GOF_RADIX];        // global position of this chunk's first key of each digit
   __shared__ uint32_t s_lbase[GOF_RADIX];        // chunk-local position of the first key of each digit
+  constexpr int CHUNK = THREADS * ITEMS;
   __shared__ KeyT s_keys[CHUNK];
   __shared__ uint32_t s_vals[CHUNK];
   __shared__ uint32_t s_chunk;
@@ -280,12 +280,19 @@ struct SortScratch {
   uint32_t* status;    // [4][chunk groups][256][4]: look-back status words (lookback_digit)
   size_t pass_words;   // words per pass in status
 };
+int sort_keys_per_thread() {
+  static int k = 0;
+  if (!k) { const char* e = getenv("GOF_SORT_KEYS"); k = (e && atoi(e) == 16) ? 16 : 8; }
+  return k;
+}
+size_t sort_chunks(size_t n) { const size_t c = (size_t)THREADS * sort_keys_per_thread(); return (n + c - 1) / c; }
+
 SortScratch carve_sort_scratch(uint32_t* scratch, size_t n) {
   SortScratch s;
   s.ghist = scratch;
   s.tickets = scratch + 4 * GOF_RADIX;
   s.status = scratch + GOF_SORT_HEAD_BYTES / 4;
-  s.pass_words = (size_t)((gof_sort_blocks(n) + 3) / 4 + 1) * GOF_RADIX * 4;
+  s.pass_words = (size_t)((sort_chunks(n) + 3) / 4 + 1) * GOF_RADIX * 4;
   return s;
 }
 
@@ -304,12 +311,18 @@ void split_digits(int nbits, Digits* dg) {   // as evenly as possible, low digit
 template <typename KeyT>
 int onesweep_passes(KeyT* ka, KeyT* kb, uint32_t* va, uint32_t* vb, size_t n, const Digits& dg, const SortScratch& sc, bool debug,
                     cudaStream_t st) {
-  const int nb = gof_sort_blocks(n);
+  const unsigned nb = (unsigned)sort_chunks(n);
+  const bool k16 = sort_keys_per_thread() == 16;
   for (int p = 0; p < dg.passes; ++p) {
     const bool a2b = (p % 2 == 0);
-    GOF_LAUNCH("radix_onesweep", st, k_onesweep<KeyT><<<nb, THREADS, 0, st>>>(
-        a2b ? ka : kb, a2b ? va : vb, a2b ? kb : ka, a2b ? vb : va, n, dg.shift[p], dg.mask[p], sc.ghist + p * GOF_RADIX,
-        sc.status + (size_t)p * sc.pass_words, sc.tickets + p));
+    if (k16)
+      GOF_LAUNCH("radix_onesweep", st, (k_onesweep<KeyT, 16><<<nb, THREADS, 0, st>>>(
+          a2b ? ka : kb, a2b ? va : vb, a2b ? kb : ka, a2b ? vb : va, n, dg.shift[p], dg.mask[p], sc.ghist + p * GOF_RADIX,
+          sc.status + (size_t)p * sc.pass_words, sc.tickets + p)));
+    else
+      GOF_LAUNCH("radix_onesweep", st, (k_onesweep<KeyT, 8><<<nb, THREADS, 0, st>>>(
+          a2b ? ka : kb, a2b ? va : vb, a2b ? kb : ka, a2b ? vb : va, n, dg.shift[p], dg.mask[p], sc.ghist + p * GOF_RADIX,
+          sc.status + (size_t)p * sc.pass_words, sc.tickets + p)));
     GOF_LAUNCH_CHECK(debug, st);
   }
   return GOF_OK;

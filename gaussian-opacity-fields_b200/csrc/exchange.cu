@@ -57,23 +57,33 @@ __global__ void __launch_bounds__(512) k_p2p_allreduce_any(const PeerPtrs a, int
 // back their sum -- reduced inside the switch -- and multimem.st pushes the result to all of them: per GPU one bucket's worth of
 // NVLink traffic in each direction instead of 2 (N-1)/N buckets over peer loads/stores.  Rank r handles the r-th 1/N slice; the
 // MAX tail holds non-negative floats, whose bit patterns order like unsigned integers (f32 has no multimem max).
+__device__ __forceinline__ float4 mm_ld_add(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st(float4* p, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __global__ void __launch_bounds__(512) k_nvls_allreduce(float4* mc, size_t begin, size_t end, size_t sum_end) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
-    float4* p = mc + i;
-    if (i < sum_end) {
-      float4 v;
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    } else {
-      uint32_t* q = reinterpret_cast<uint32_t*>(p);
+  size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // SUM part, four independent 16-byte reductions in flight per thread (a switch round trip is microseconds)
+  const size_t s_end = sum_end < end ? sum_end : end;
+  for (; i + 3 * stride < s_end; i += 4 * stride) {
+    const float4 a = mm_ld_add(mc + i), b = mm_ld_add(mc + i + stride), c = mm_ld_add(mc + i + 2 * stride), d = mm_ld_add(mc + i + 3 * stride);
+    mm_st(mc + i, a); mm_st(mc + i + stride, b); mm_st(mc + i + 2 * stride, c); mm_st(mc + i + 3 * stride, d);
+  }
+  for (; i < s_end; i += stride) mm_st(mc + i, mm_ld_add(mc + i));
+  // MAX tail (continues on the same index lattice)
+  for (; i < end; i += stride) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(mc + i);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t u;
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(u) : "l"(q + k) : "memory");
-        asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(q + k), "r"(u) : "memory");
-      }
+    for (int k = 0; k < 4; ++k) {
+      uint32_t u;
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(u) : "l"(q + k) : "memory");
+      asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(q + k), "r"(u) : "memory");
     }
   }
 }

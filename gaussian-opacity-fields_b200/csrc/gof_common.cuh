@@ -179,8 +179,10 @@ static inline int gof_sort_blocks(size_t n) { return (int)((n + GOF_SORT_CHUNK -
 // and per pass one decoupled-look-back status word per (chunk, digit).  (The pre-onesweep kernels, kept for A/B runs under
 // GOF_BINNING=legacy, need 256 * (blocks + 1) words of it.)
 #define GOF_SORT_HEAD_BYTES (4 * GOF_RADIX * 4 + 256)
+#define GOF_SORT_MIN_CHUNK 2048   /* the one-sweep passes may run with 8 keys per thread: size the status words for that */
 static inline size_t gof_sort_scratch_bytes(size_t n) {
-  return (size_t)GOF_SORT_HEAD_BYTES + (size_t)4 * (size_t)(gof_sort_blocks(n) + 8) * GOF_RADIX * 4;
+  const size_t blocks = (n + GOF_SORT_MIN_CHUNK - 1) / GOF_SORT_MIN_CHUNK;
+  return (size_t)GOF_SORT_HEAD_BYTES + (size_t)4 * (blocks + 8) * GOF_RADIX * 4;
 }
 
 struct GofGeomLayout {      // "geomBuffer": everything sized by P
@@ -312,7 +314,7 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
 int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const char* geom,
                                    const GofGeomLayout& L, const int* radii, float* dL_dmean2D, float* dL_dopacity,
                                    float* dL_dcolor, float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
-                                   float* dL_drot, float* dens_sum, float* dens_max, cudaStream_t st);
+                                   float* dL_drot, float* dL_dcov3D, float* dens_sum, float* dens_max, cudaStream_t st);
 int gof_launch_mark_visible(int P, const float* means3D, const float* vm, unsigned char* present,
                             cudaStream_t st);
 

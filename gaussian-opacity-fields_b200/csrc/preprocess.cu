@@ -236,6 +236,7 @@ struct PreBwdArgs {
   float* dL_dsh;
   float* dL_dscale;
   float* dL_drot;
+  float* dL_dcov3D;         // optional [P][6]: written as zeros
   float* dens_sum;          // optional [P][3]: |dL_dmean2D.xy|, |dL_dmean2D.z|, 1 for visible Gaussians (gof_rasterize_backward_stats)
   float* dens_max;          // optional [P][2]: |dL_dmean2D.z|, radius
 };
@@ -275,8 +276,36 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool active = idx < a.P && a.radii[idx] > 0;
   const unsigned active_mask = __ballot_sync(0xffffffffu, active);
-  if (active_mask == 0u) return;   // whole warp invisible
   float* my_dsh = &s_dsh[warp][lane * K8_ROW];
+  // EVERY output element of every Gaussian is written by this kernel (zeros for Gaussians this view does not see): callers may
+  // hand in uninitialised tensors -- the reference zero-fills ten tensors per backward (rasterize_points.cu:161-170), which at
+  // 1 M Gaussians is 324 MB of memset in front of the kernels.
+  if (!active && idx < a.P) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a.dL_dv2g[10 * (size_t)idx + k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a.dL_dcolor[3 * (size_t)idx + c] = 0.f;
+      a.dL_dmean2D[3 * (size_t)idx + c] = 0.f;
+      a.dL_dmean3D[3 * (size_t)idx + c] = 0.f;
+    }
+    a.dL_dopacity[idx] = 0.f;
+    if (a.dens_sum != nullptr) {
+      a.dens_sum[3 * (size_t)idx] = 0.f; a.dens_sum[3 * (size_t)idx + 1] = 0.f; a.dens_sum[3 * (size_t)idx + 2] = 0.f;
+      a.dens_max[2 * (size_t)idx] = 0.f; a.dens_max[2 * (size_t)idx + 1] = 0.f;
+    }
+  }
+  if (idx < a.P) {
+    if (a.dL_dcov3D != nullptr) {   // never receives a gradient (backward.cu:991-1007: EWA backward disabled)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * (size_t)idx + k] = 0.f;
+    }
+    const bool chain = active && a.scales != nullptr && a.rotations != nullptr;   // the view2gaussian chain rule writes these two
+    if (!chain) {
+      if (a.dL_dscale != nullptr) { a.dL_dscale[3 * (size_t)idx] = 0.f; a.dL_dscale[3 * (size_t)idx + 1] = 0.f; a.dL_dscale[3 * (size_t)idx + 2] = 0.f; }
+      if (a.dL_drot != nullptr) reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 
   if (active) {
   // the blend kernel's 64-byte accumulator row -> the public gradient tensors
@@ -518,25 +547,30 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
   a.dL_dmean3D[3 * idx + 2] = dmean[2];
   }   // active
 
-  // ---- the warp's dL_dsh rows: shared memory -> global, contiguous ----
+  // ---- the warp's dL_dsh rows: shared memory -> global, contiguous; rows of invisible Gaussians and the coefficients above
+  // the active degree (backward.cu:20-139 writes degree <= D only) are written as zeros ----
   if (a.shs != nullptr) {
     __syncwarp();
-    const int nw = 3 * (a.D + 1) * (a.D + 1);             // floats written per Gaussian (backward.cu writes degree <= D only)
+    const int nw = 3 * (a.D + 1) * (a.D + 1);             // floats carrying a gradient per Gaussian
+    const int row = a.M * 3;                              // floats per Gaussian in dL_dsh
     const size_t g0 = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32;   // first Gaussian of this warp
+    const int in_range = (int)min((size_t)32, (size_t)a.P > g0 ? (size_t)a.P - g0 : (size_t)0);
     if (a.M == 16 && nw == 48) {
       float4* dst = reinterpret_cast<float4*>(a.dL_dsh + g0 * 48);
 #pragma unroll 4
-      for (int i = lane; i < 32 * 12; i += 32) {
+      for (int i = lane; i < in_range * 12; i += 32) {
         const int g = i / 12, j = (i - g * 12) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((active_mask >> g) & 1u) {
           const float* r = &s_dsh[warp][g * K8_ROW + j];
-          dst[i] = make_float4(r[0], r[1], r[2], r[3]);
+          v = make_float4(r[0], r[1], r[2], r[3]);
         }
+        dst[i] = v;
       }
     } else {
-      for (int i = lane; i < 32 * nw; i += 32) {
-        const int g = i / nw, j = i - g * nw;
-        if ((active_mask >> g) & 1u) a.dL_dsh[(g0 + g) * (size_t)a.M * 3 + j] = s_dsh[warp][g * K8_ROW + j];
+      for (int i = lane; i < in_range * row; i += 32) {
+        const int g = i / row, j = i - g * row;
+        a.dL_dsh[(g0 + g) * (size_t)row + j] = (((active_mask >> g) & 1u) && j < nw) ? s_dsh[warp][g * K8_ROW + j] : 0.f;
       }
     }
   }
@@ -579,7 +613,7 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
 int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const char* geom,
                                    const GofGeomLayout& L, const int* radii, float* dL_dmean2D, float* dL_dopacity,
                                    float* dL_dcolor, float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
-                                   float* dL_drot, float* dens_sum, float* dens_max, cudaStream_t st) {
+                                   float* dL_drot, float* dL_dcov3D, float* dens_sum, float* dens_max, cudaStream_t st) {
   (void)v;
   PreBwdArgs a;
   a.P = s->P; a.D = s->D; a.M = s->M;
@@ -590,7 +624,7 @@ int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const
   a.splat = reinterpret_cast<const GofSplat*>(geom + L.splat);
   a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity;
   a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g; a.dL_dmean3D = dL_dmean3D; a.dL_dsh = dL_dsh;
-  a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+  a.dL_dscale = dL_dscale; a.dL_drot = dL_drot; a.dL_dcov3D = dL_dcov3D;
   a.dens_sum = (dens_sum && dens_max) ? dens_sum : nullptr; a.dens_max = a.dens_sum ? dens_max : nullptr;
   GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + K8_THREADS - 1) / K8_THREADS, K8_THREADS, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);

@@ -244,8 +244,10 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     M = s.M
     o = dict(dtype=means3D.dtype, device=means3D.device)
 
-    # One zero-filled block for all gradient tensors (one fill instead of the reference's ten torch::zeros,
-    # rasterize_points.cu:161-170); every tensor is a contiguous, 256-byte aligned view of it.
+    # One UNINITIALISED block for all gradient tensors (the reference zero-fills ten tensors, rasterize_points.cu:161-170: 324 MB
+    # of memset per backward at 1 M Gaussians): the library's backward writes every element of every output itself -- zeros for
+    # Gaussians the view does not see, for dL_dcov3D and for SH coefficients above the active degree.  Every tensor is a
+    # contiguous, 256-byte aligned view of the block.
     shapes = dict(dmeans3D=(P, 3), dmeans2D=(P, 3), dcolors=(P, 3), dopacity=(P, 1), dcov3D=(P, 6), dsh=(P, M, 3),
                   dscales=(P, 3), drot=(P, 4), dv2g=(P, 10))
     need = {k: v for k, v in shapes.items() if not (_out is not None and k in _out)}
@@ -256,7 +258,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         for d in shp:
             n *= d
         total += (n + 63) // 64 * 64
-    block = torch.zeros(max(total, 1), **o)
+    block = torch.empty(max(total, 1), **o) if P else torch.zeros(max(total, 1), **o)
 
     def _z(name, shape):
         # `_out` (extension, used by gof_dp.GradBucket): pre-zeroed, contiguous destination tensors, e.g. views

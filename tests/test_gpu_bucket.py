@@ -67,3 +67,31 @@ def test_misaligned_inputs_are_accepted():
     g = _C.rasterize_gaussians_backward(*_util.bwd_args(tuple(fa), out[2], out[3], out[0], out[4], out[5], grad))
     torch.cuda.synchronize()
     assert torch.isfinite(g[5]).all()
+
+
+def test_backward_fills_uninitialised_outputs():
+    """The backward writes EVERY element of its outputs (zeros for unseen Gaussians, for dL_dcov3D, for SH coefficients above the
+    active degree): garbage-filled `_out` tensors end up identical to the plain call's."""
+    from diff_gaussian_rasterization import _C
+    dev = torch.device("cuda")
+    P = 20_001
+    cam, gs = gof_synth.make_scene(dict(P=P, width=256, height=192, seed=23), view=40)      # many Gaussians outside this view
+    gs = dict(gs)
+    fa = _util.fwd_args(cam, gs, dev, sh_degree=1)                                          # degree 1 of 16 coefficients: tail columns
+    R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
+    assert int((radii == 0).sum()) > 100
+    grad = torch.randn(9, 192, 256, generator=torch.Generator().manual_seed(5)).to(dev)
+    shapes = dict(dmeans3D=(P, 3), dmeans2D=(P, 3), dcolors=(P, 3), dopacity=(P, 1), dcov3D=(P, 6), dsh=(P, 16, 3), dscales=(P, 3),
+                  drot=(P, 4), dv2g=(P, 10), dens_sum=(P, 3), dens_max=(P, 2))
+    out = {k: torch.full(s, float("nan"), device=dev) for k, s in shapes.items()}
+    g = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=out)
+    torch.cuda.synchronize()
+    for k, t in out.items():
+        assert torch.isfinite(t).all(), k
+    inv = radii == 0
+    for k in ("dmeans3D", "dmeans2D", "dcolors", "dopacity", "dsh", "dscales", "drot", "dv2g", "dens_sum", "dens_max"):
+        assert float(out[k][inv].abs().max()) == 0.0, k
+    assert float(out["dcov3D"].abs().max()) == 0.0
+    assert float(out["dsh"][:, 4:, :].abs().max()) == 0.0 and float(out["dsh"][:, :4, :].abs().max()) > 0.0
+    plain = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad))
+    assert _util.rel_err(g[5], plain[5])[0] < 1e-5 and _util.rel_err(g[2], plain[2])[0] < 1e-5

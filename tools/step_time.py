@@ -31,7 +31,7 @@ bucket = gof_dp.GradBucket(P, 16, dev)
 def step(i):
     fa = fas[i % len(fas)]
     R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
-    bucket.zero_()
+    # (the backward writes every element of its outputs: no zero fill)
     _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=bucket.views)
     return R
 

@@ -23,7 +23,7 @@ def step(i, log=None):
     t0 = time.perf_counter()
     R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
     t1 = time.perf_counter()
-    bucket.zero_()
+    # (the backward writes every element of its outputs: no zero fill)
     g = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=bucket.views)
     t2 = time.perf_counter()
     if log is not None:
