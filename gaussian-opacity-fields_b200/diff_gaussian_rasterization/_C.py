@@ -215,8 +215,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     if s.P and not means3D.is_cuda:
         raise RuntimeError("gof_b200: means3D must be a CUDA tensor (no CPU path)")
     with torch.cuda.device(dev if means3D.is_cuda else torch.cuda.current_device()):
-        out_color = torch.zeros((9, int(image_height), int(image_width)), dtype=torch.float32, device=dev)
-        radii = torch.zeros((s.P,), dtype=torch.int32, device=dev)
+        # the forward writes every pixel of the 9 channels and every radius (the reference zero-fills both, rasterize_points.cu:70-72)
+        alloc = torch.empty if s.P != 0 else torch.zeros
+        out_color = alloc((9, int(image_height), int(image_width)), dtype=torch.float32, device=dev)
+        radii = alloc((s.P,), dtype=torch.int32, device=dev)
         sdev = dev if means3D.is_cuda else torch.device("cuda")
         geom, binning, img = _Scratch(sdev, "geom"), _Scratch(sdev, "binning", 1.25), _Scratch(sdev, "image")
         rendered = ctypes.c_int(0)
