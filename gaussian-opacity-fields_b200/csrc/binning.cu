@@ -282,7 +282,8 @@ struct SortScratch {
 };
 int sort_keys_per_thread() {
   static int k = 0;
-  if (!k) { const char* e = getenv("GOF_SORT_KEYS"); k = (e && atoi(e) == 8) ? 8 : 16;   // 16 keys per thread measured faster (0.175 vs 0.185 ms for the six passes at C3) }
+  // 16 keys per thread measured faster than 8 (0.175 vs 0.185 ms for the six passes at C3)
+  if (!k) { const char* e = getenv("GOF_SORT_KEYS"); k = (e && atoi(e) == 8) ? 8 : 16; }
   return k;
 }
 size_t sort_chunks(size_t n) { const size_t c = (size_t)THREADS * sort_keys_per_thread(); return (n + c - 1) / c; }

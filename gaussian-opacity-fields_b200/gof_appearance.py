@@ -3,16 +3,70 @@
 GEMM-shaped math on the path.
 
 Same module structure and parameter names as the reference (conv1, up1.conv ... up4.conv, conv2, conv3), so a reference
-checkpoint's `appearance_network` state_dict loads unchanged.  The convolutions run through torch (cuDNN; TF32 tensor-core math
-is the reference's own default, torch.backends.cudnn.allow_tf32): at 1080p the network costs ~16 GFLOP forward, dominated by
-the 16->16 convolution at full resolution, and is kept on the library path -- DESIGN.md states its measured share of a C4 step.
+checkpoint's `appearance_network` state_dict loads unchanged.  Forward and data gradients of the convolutions run through torch
+(cuDNN; TF32 tensor-core math is the reference's own default, torch.backends.cudnn.allow_tf32); the WEIGHT gradients of the
+few-channel layers at (near) full resolution -- where cuDNN's generic fp32 engine took 40 % of the appearance step -- come from
+the library's own kernel (csrc/conv_wgrad.cu, `_Conv3x3`).  DESIGN.md states the measured share of a C4 step.
 What this module adds over the reference's formulation: the per-view tensors the loss re-creates every iteration (crop window,
 the embedding broadcast to the 1/32 grid) are built without the `repeat().permute()` copy, and `appearance_grads_flat` /
 `load_flat_grads_` pack the network's and the embedding's gradients into the view-parallel gradient bucket
 (gof_dp.GradBucket(extra_sum=...)) so that they travel in the same exchange as the Gaussian gradients."""
+import ctypes
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+# A/B switches (developer use): GOF_APP_WGRAD=0 -> cuDNN's weight gradients, GOF_APP_NHWC=1 -> channels-last activations
+_USE_WGRAD = os.environ.get("GOF_APP_WGRAD", "1") != "0"
+_USE_NHWC = os.environ.get("GOF_APP_NHWC", "0") == "1"
+_WGRAD_PAIRS = {(16, 16), (3, 16), (16, 8)}          # (C_out, C_in) pairs csrc/conv_wgrad.cu is instantiated for
+_lib = None
+
+
+def _wgrad_lib():
+    global _lib
+    if _lib is None:
+        from diff_gaussian_rasterization import _C
+        _lib = _C._lib
+        _lib.gof_conv3x3_wgrad.restype = ctypes.c_int
+        _lib.gof_conv3x3_wgrad.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5
+    return _lib
+
+
+class _Conv3x3(torch.autograd.Function):
+    """3x3 / stride 1 / pad 1 convolution whose WEIGHT and BIAS gradients come from the library's kernel (csrc/conv_wgrad.cu):
+    for the few-channel, full-resolution layers at the network's tail cuDNN falls back to a generic fp32 weight-gradient engine
+    that alone costs 2.1 ms of a 5.2 ms appearance step on B200 (profiles/r2_appearance_profile_cudnn.txt).  Forward and data
+    gradient stay on cuDNN."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return F.conv2d(x, weight, bias, padding=1)
+
+    @staticmethod
+    def backward(ctx, gy):
+        from diff_gaussian_rasterization import _C
+        x, weight = ctx.saved_tensors
+        gx = torch.nn.grad.conv2d_input(x.shape, weight, gy, padding=1) if ctx.needs_input_grad[0] else None
+        xc, gc = x.detach().contiguous(), gy.contiguous()
+        dW = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+        db = torch.zeros(weight.shape[0], dtype=weight.dtype, device=weight.device)
+        with torch.cuda.device(x.device):
+            _C._check(_wgrad_lib().gof_conv3x3_wgrad(int(weight.shape[0]), int(weight.shape[1]), int(x.shape[2]), int(x.shape[3]), xc.data_ptr(),
+                                                     gc.data_ptr(), dW.data_ptr(), db.data_ptr(), _C._stream()))
+        return gx, dW, db
+
+
+def conv3x3(x, conv):
+    """`conv(x)` for an nn.Conv2d(3x3, stride 1, pad 1), through _Conv3x3 when its weight gradient is worth taking over."""
+    w = conv.weight
+    if (_USE_WGRAD and x.is_cuda and x.dtype == torch.float32 and x.shape[0] == 1 and (int(w.shape[0]), int(w.shape[1])) in _WGRAD_PAIRS
+            and x.shape[2] * x.shape[3] >= 128 * 128 and conv.bias is not None and torch.is_grad_enabled() and w.requires_grad):
+        return _Conv3x3.apply(x, w, conv.bias)
+    return conv(x)
 
 
 class UpsampleBlock(nn.Module):   # scene/appearance_network.py:5-16
@@ -23,7 +77,7 @@ class UpsampleBlock(nn.Module):   # scene/appearance_network.py:5-16
         self.relu = nn.ReLU()
 
     def forward(self, x):
-        return self.relu(self.conv(self.pixel_shuffle(x)))
+        return self.relu(conv3x3(self.pixel_shuffle(x), self.conv))
 
 
 class AppearanceNetwork(nn.Module):   # scene/appearance_network.py:18-46
@@ -40,16 +94,13 @@ class AppearanceNetwork(nn.Module):   # scene/appearance_network.py:18-46
         self.sigmoid = nn.Sigmoid()
 
     def forward(self, x):
-        if x.is_cuda:
-            # NHWC activations: with 8..16 channels at full resolution cuDNN's NCHW kernels run far from the tensor cores; the
-            # channels-last ones (TF32, like the reference's default math) are its fast path.  Parameters may stay as they are
-            # (cuDNN transforms the 3x3 filters on the fly); results agree to TF32 rounding either way.
+        if x.is_cuda and _USE_NHWC:      # measured on B200: no gain (cuDNN converts back and forth around its NCHW engines)
             x = x.contiguous(memory_format=torch.channels_last)
         x = self.relu(self.conv1(x))
         x = self.up4(self.up3(self.up2(self.up1(x))))
         x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
-        x = self.relu(self.conv2(x))
-        return self.sigmoid(self.conv3(x))
+        x = self.relu(conv3x3(x, self.conv2))
+        return self.sigmoid(conv3x3(x, self.conv3))
 
 
 def crop_window(origH, origW):

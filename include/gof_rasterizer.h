@@ -267,6 +267,10 @@ GOF_API int gof_densify_emit(int P, const uint32_t* flags, const uint32_t* offse
                              int32_t* src_index, unsigned char* kind, float* new_xyz, float* new_scaling_raw, void* stream);
 GOF_API int gof_gather_rows_f32(const float* src, int row_floats, const int32_t* src_index, const unsigned char* kind, size_t n_out,
                                 int zero_new, float* dst, void* stream);
+/* Weight / bias gradient of a 3x3, stride-1, pad-1 convolution with few channels at full image resolution (the tail of the
+ * reference's AppearanceNetwork, scene/appearance_network.py:28-29): x [CI,H,W], gy [CO,H,W] -> dW [CO,CI,3,3], db [CO] or NULL,
+ * ACCUMULATED into (zero first).  Channel pairs CI->CO: 16->16, 16->3, 8->16. */
+GOF_API int gof_conv3x3_wgrad(int CO, int CI, int H, int W, const float* x, const float* gy, float* dW, float* db, void* stream);
 GOF_API int gof_adam_step(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, double lr, double beta1,
                           double beta2, double eps, int step, void* stream);
 

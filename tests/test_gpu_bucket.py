@@ -95,3 +95,25 @@ def test_backward_fills_uninitialised_outputs():
     assert float(out["dsh"][:, 4:, :].abs().max()) == 0.0 and float(out["dsh"][:, :4, :].abs().max()) > 0.0
     plain = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad))
     assert _util.rel_err(g[5], plain[5])[0] < 1e-5 and _util.rel_err(g[2], plain[2])[0] < 1e-5
+
+
+def test_conv3x3_weight_gradient_kernel():
+    """csrc/conv_wgrad.cu (the appearance network's tail) against a float64 evaluation of the same convolution's weight / bias
+    gradient, for every instantiated channel pair, on image sizes that are not tile multiples."""
+    import gof_appearance
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(3)
+    for (co, ci), (H, W) in (((16, 16), (203, 333)), ((3, 16), (130, 200)), ((16, 8), (264, 129))):
+        conv = torch.nn.Conv2d(ci, co, 3, padding=1).to(dev)
+        x = torch.randn(1, ci, H, W, generator=gen).to(dev).requires_grad_(True)
+        gy = torch.randn(1, co, H, W, generator=gen).to(dev)
+        y = gof_appearance.conv3x3(x, conv)
+        assert y.grad_fn is not None and "Conv3x3" in type(y.grad_fn).__name__
+        y.backward(gy)
+        conv64 = torch.nn.Conv2d(ci, co, 3, padding=1).to(dev).double()
+        conv64.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+        x64 = x.detach().double().requires_grad_(True)
+        conv64(x64).backward(gy.double())
+        assert _util.rel_err(conv.weight.grad, conv64.weight.grad)[0] < 2e-5, (co, ci)
+        assert _util.rel_err(conv.bias.grad, conv64.bias.grad)[0] < 2e-5
+        assert _util.rel_err(x.grad, x64.grad)[0] < 5e-3          # cuDNN's TF32 data gradient
