@@ -12,6 +12,8 @@ sys.path.insert(0, os.path.join(ROOT, "gaussian-opacity-fields_b200"))
 import gof_appearance  # noqa: E402
 
 dev = torch.device("cuda")
+if os.environ.get("GOF_APP_CUDNN_BENCH") == "1":
+    torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 net = gof_appearance.AppearanceNetwork(67, 3).to(dev)
 emb = (torch.randn(64, device=dev) * 1e-4).requires_grad_(True)
@@ -41,4 +43,4 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=90))
