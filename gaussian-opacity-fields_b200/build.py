@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "diff_gaussian_rasterization")
 LIB = os.path.join(OUT_DIR, "libgof_b200.so")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "binning_legacy.cu", "render_fwd.cu", "render_bwd.cu", "integrate.cu", "tetmesh.cu", "exchange.cu", "view_loss.cu", "param_ops.cu", "filter3d.cu", "densify.cu", "conv_wgrad.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "binning_legacy.cu", "render_fwd.cu", "render_bwd.cu", "integrate.cu", "tetmesh.cu", "exchange.cu", "view_loss.cu", "param_ops.cu", "filter3d.cu", "densify.cu", "conv_wgrad.cu", "sh_views.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

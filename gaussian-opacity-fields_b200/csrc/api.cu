@@ -308,6 +308,17 @@ extern "C" int gof_rasterize_backward_stats(const gof_scene_t* s, int num_render
                                             float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                                             float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                                             float* dL_dview2gaussian, float* dens_sum, float* dens_max, void* stream) {
+  return gof_rasterize_backward_dp(s, num_rendered, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dmean2D, dL_dconic,
+                                   dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dview2gaussian, dens_sum,
+                                   dens_max, nullptr, nullptr, stream);
+}
+
+extern "C" int gof_rasterize_backward_dp(const gof_scene_t* s, int num_rendered, const int* radii, void* geom_buffer,
+                                         const void* binning_buffer, const void* image_buffer, const float* dL_dpix,
+                                         float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                                         float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                         float* dL_dview2gaussian, float* dens_sum, float* dens_max, float* sh_rgb, float* sh_hdr,
+                                         void* stream) {
   (void)dL_dconic;
   int rc = validate_scene(s);
   if (rc != GOF_OK) return rc;
@@ -317,7 +328,11 @@ extern "C" int gof_rasterize_backward_stats(const gof_scene_t* s, int num_render
     gof_set_error("backward: NULL argument");
     return GOF_E_INVALID;
   }
-  if (s->shs && !dL_dsh) { gof_set_error("backward: dL_dsh required with SHs"); return GOF_E_INVALID; }
+  if (s->shs && !dL_dsh && !(sh_rgb && sh_hdr)) { gof_set_error("backward: dL_dsh (or sh_rgb + sh_hdr) required with SHs"); return GOF_E_INVALID; }
+  if ((sh_rgb != nullptr) != (sh_hdr != nullptr) || (sh_rgb && !s->shs)) {
+    gof_set_error("backward: sh_rgb and sh_hdr come together and need SHs");
+    return GOF_E_INVALID;
+  }
   if (s->scales && s->rotations && (!dL_dscale || !dL_drot)) {
     gof_set_error("backward: dL_dscale / dL_drot required");
     return GOF_E_INVALID;
@@ -334,7 +349,7 @@ extern "C" int gof_rasterize_backward_stats(const gof_scene_t* s, int num_render
                                        st)) != GOF_OK)
     return rc;
   return gof_launch_preprocess_backward(s, v, geom, GL, radii, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dview2gaussian, dL_dmean3D,
-                                        dL_dsh, dL_dscale, dL_drot, dL_dcov3D, dens_sum, dens_max, st);
+                                        dL_dsh, dL_dscale, dL_drot, dL_dcov3D, dens_sum, dens_max, sh_rgb, sh_hdr, st);
 }
 
 extern "C" int gof_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -239,6 +239,8 @@ struct PreBwdArgs {
   float* dL_dcov3D;         // optional [P][6]: written as zeros
   float* dens_sum;          // optional [P][3]: |dL_dmean2D.xy|, |dL_dmean2D.z|, 1 for visible Gaussians (gof_rasterize_backward_stats)
   float* dens_max;          // optional [P][2]: |dL_dmean2D.z|, radius
+  float* sh_rgb;            // optional [P][3]: the clamp-masked dL_dRGB the SH gradient is the outer product of (view-parallel exchange,
+  float* sh_hdr;            //   csrc/sh_views.cu); sh_hdr[0..3] = camera centre, active degree.  dL_dsh may then be NULL.
 };
 
 // m[c][r] column-major helpers mirroring the glm products used by backward.cu:381-587.  The chain rule through
@@ -290,10 +292,14 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
       a.dL_dmean3D[3 * (size_t)idx + c] = 0.f;
     }
     a.dL_dopacity[idx] = 0.f;
+    if (a.sh_rgb != nullptr) { a.sh_rgb[3 * (size_t)idx] = 0.f; a.sh_rgb[3 * (size_t)idx + 1] = 0.f; a.sh_rgb[3 * (size_t)idx + 2] = 0.f; }
     if (a.dens_sum != nullptr) {
       a.dens_sum[3 * (size_t)idx] = 0.f; a.dens_sum[3 * (size_t)idx + 1] = 0.f; a.dens_sum[3 * (size_t)idx + 2] = 0.f;
       a.dens_max[2 * (size_t)idx] = 0.f; a.dens_max[2 * (size_t)idx + 1] = 0.f;
     }
+  }
+  if (idx == 0 && a.sh_hdr != nullptr) {
+    a.sh_hdr[0] = a.cam_pos[0]; a.sh_hdr[1] = a.cam_pos[1]; a.sh_hdr[2] = a.cam_pos[2]; a.sh_hdr[3] = (float)a.D;
   }
   if (idx < a.P) {
     if (a.dL_dcov3D != nullptr) {   // never receives a gradient (backward.cu:991-1007: EWA backward disabled)
@@ -473,17 +479,16 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
 
     float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
 #define SH(k, c) sh[3 * (k) + (c)]
-#define DSH(k, w)                                  \
-  {                                                \
-    dsh[3 * (k) + 0] = (w) * dRGB[0];              \
-    dsh[3 * (k) + 1] = (w) * dRGB[1];              \
-    dsh[3 * (k) + 2] = (w) * dRGB[2];              \
-  }
-    DSH(0, GOF_SH_C0);
+    if (a.sh_rgb != nullptr) { a.sh_rgb[3 * (size_t)idx] = dRGB[0]; a.sh_rgb[3 * (size_t)idx + 1] = dRGB[1]; a.sh_rgb[3 * (size_t)idx + 2] = dRGB[2]; }
+    if (a.dL_dsh != nullptr) {
+      float w[16];
+      gof_sh_grad_weights(a.D, x, y, z, w);
+      const int nk = (a.D + 1) * (a.D + 1);
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < nk) { dsh[3 * k] = w[k] * dRGB[0]; dsh[3 * k + 1] = w[k] * dRGB[1]; dsh[3 * k + 2] = w[k] * dRGB[2]; }
+    }
     if (a.D > 0) {
-      DSH(1, -GOF_SH_C1 * y);
-      DSH(2, GOF_SH_C1 * z);
-      DSH(3, -GOF_SH_C1 * x);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         dRGBdx[c] = -GOF_SH_C1 * SH(3, c);
@@ -492,11 +497,6 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
       }
       if (a.D > 1) {
         const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        DSH(4, GOF_SH_C2_0 * xy);
-        DSH(5, GOF_SH_C2_1 * yz);
-        DSH(6, GOF_SH_C2_2 * (2.f * zz - xx - yy));
-        DSH(7, GOF_SH_C2_3 * xz);
-        DSH(8, GOF_SH_C2_4 * (xx - yy));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           dRGBdx[c] += GOF_SH_C2_0 * y * SH(4, c) + GOF_SH_C2_2 * 2.f * -x * SH(6, c) + GOF_SH_C2_3 * z * SH(7, c) +
@@ -506,13 +506,6 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
           dRGBdz[c] += GOF_SH_C2_1 * y * SH(5, c) + GOF_SH_C2_2 * 2.f * 2.f * z * SH(6, c) + GOF_SH_C2_3 * x * SH(7, c);
         }
         if (a.D > 2) {
-          DSH(9, GOF_SH_C3_0 * y * (3.f * xx - yy));
-          DSH(10, GOF_SH_C3_1 * xy * z);
-          DSH(11, GOF_SH_C3_2 * y * (4.f * zz - xx - yy));
-          DSH(12, GOF_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
-          DSH(13, GOF_SH_C3_4 * x * (4.f * zz - xx - yy));
-          DSH(14, GOF_SH_C3_5 * z * (xx - yy));
-          DSH(15, GOF_SH_C3_6 * x * (xx - 3.f * yy));
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             dRGBdx[c] += (GOF_SH_C3_0 * SH(9, c) * 3.f * 2.f * xy + GOF_SH_C3_1 * SH(10, c) * yz +
@@ -531,7 +524,6 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
       }
     }
 #undef SH
-#undef DSH
     const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
     const float ddy = dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2];
     const float ddz = dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2];
@@ -549,7 +541,7 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
 
   // ---- the warp's dL_dsh rows: shared memory -> global, contiguous; rows of invisible Gaussians and the coefficients above
   // the active degree (backward.cu:20-139 writes degree <= D only) are written as zeros ----
-  if (a.shs != nullptr) {
+  if (a.shs != nullptr && a.dL_dsh != nullptr) {
     __syncwarp();
     const int nw = 3 * (a.D + 1) * (a.D + 1);             // floats carrying a gradient per Gaussian
     const int row = a.M * 3;                              // floats per Gaussian in dL_dsh
@@ -613,7 +605,8 @@ int gof_launch_preprocess(const gof_scene_t* s, const GofView& v, char* geom, co
 int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const char* geom,
                                    const GofGeomLayout& L, const int* radii, float* dL_dmean2D, float* dL_dopacity,
                                    float* dL_dcolor, float* dL_dv2g, float* dL_dmean3D, float* dL_dsh, float* dL_dscale,
-                                   float* dL_drot, float* dL_dcov3D, float* dens_sum, float* dens_max, cudaStream_t st) {
+                                   float* dL_drot, float* dL_dcov3D, float* dens_sum, float* dens_max, float* sh_rgb, float* sh_hdr,
+                                   cudaStream_t st) {
   (void)v;
   PreBwdArgs a;
   a.P = s->P; a.D = s->D; a.M = s->M;
@@ -626,6 +619,7 @@ int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const
   a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g; a.dL_dmean3D = dL_dmean3D; a.dL_dsh = dL_dsh;
   a.dL_dscale = dL_dscale; a.dL_drot = dL_drot; a.dL_dcov3D = dL_dcov3D;
   a.dens_sum = (dens_sum && dens_max) ? dens_sum : nullptr; a.dens_max = a.dens_sum ? dens_max : nullptr;
+  a.sh_rgb = s->shs ? sh_rgb : nullptr; a.sh_hdr = a.sh_rgb ? sh_hdr : nullptr;
   GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + K8_THREADS - 1) / K8_THREADS, K8_THREADS, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;

@@ -1,0 +1,105 @@
+// sh_views.cu -- the SH-gradient half of the view-parallel exchange (no reference counterpart).
+//
+// Of the 64 floats per Gaussian a view-parallel step has to combine across GPUs, 48 are dL_dsh -- and one view's dL_dsh is an
+// outer product: dL_dsh[k][c] = w_k(dir) * dL_dRGB[c] (backward.cu:45-139), dir = normalize(mean - camera centre).  Every
+// rank holds all means and can learn every rank's camera centre, so the ranks only need each other's dL_dRGB: 3 floats per
+// Gaussian and view instead of an all-reduce over 48.  This kernel forms sum_v w(dir_v) (x) rgb_v for all views v, in rank
+// order and with the products rounded before the additions -- bit-identical to adding the per-view dL_dsh tensors that
+// k_preprocess_backward would have written (it evaluates the same gof_sh_grad_weights).  The view records are read through
+// a pointer per view: local memory after an NCCL all-gather, or the peers' buckets themselves over NVLink.
+#include "gof_common.cuh"
+#include "gof_math.cuh"
+
+namespace {
+
+constexpr int SHV_THREADS = 128;
+constexpr int SHV_ROW = 49;      // 48 floats per Gaussian + 1 pad
+constexpr int SHV_MAX_VIEWS = 16;
+
+struct ShvArgs {
+  int P, M, n_views;
+  const float* means3D;
+  const float* slot[SHV_MAX_VIEWS];
+  float* dL_dsh;
+};
+
+__global__ void __launch_bounds__(SHV_THREADS) k_sh_grad_from_views(const ShvArgs a) {
+  __shared__ float s_out[SHV_THREADS / 32][32 * SHV_ROW];
+  __shared__ float s_cam[SHV_MAX_VIEWS][4];
+  if (threadIdx.x < a.n_views * 4) s_cam[threadIdx.x >> 2][threadIdx.x & 3] = __ldcg(a.slot[threadIdx.x >> 2] + (threadIdx.x & 3));
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[48];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+  int maxD = 0;
+  if (idx < a.P) {
+    const float mx = a.means3D[3 * (size_t)idx], my = a.means3D[3 * (size_t)idx + 1], mz = a.means3D[3 * (size_t)idx + 2];
+    for (int v = 0; v < a.n_views; ++v) {
+      const float* rgbp = a.slot[v] + GOF_SH_SLOT_HEADER + 3 * (size_t)idx;
+      const float r = __ldcg(rgbp), g = __ldcg(rgbp + 1), b = __ldcg(rgbp + 2);   // L2 only: may be a peer's memory
+      const int D = (int)s_cam[v][3];
+      maxD = D > maxD ? D : maxD;
+      if (r == 0.f && g == 0.f && b == 0.f) continue;   // not seen by view v (or clamped in all channels): contributes +0
+      // the direction exactly as k_preprocess_backward forms it
+      const float dox = mx - s_cam[v][0], doy = my - s_cam[v][1], doz = mz - s_cam[v][2];
+      const float len = sqrtf(dox * dox + doy * doy + doz * doz);
+      const float x = dox / len, y = doy / len, z = doz / len;
+      float w[16];
+      gof_sh_grad_weights(D, x, y, z, w);
+      const int nk = (D + 1) * (D + 1);
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < nk) {
+          acc[3 * k] = __fadd_rn(acc[3 * k], __fmul_rn(w[k], r));
+          acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], __fmul_rn(w[k], g));
+          acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], __fmul_rn(w[k], b));
+        }
+    }
+  }
+  float* mine = &s_out[warp][lane * SHV_ROW];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) mine[k] = acc[k];
+  __syncwarp();
+  // the warp's 32 consecutive Gaussians leave as one contiguous block
+  const int row = a.M * 3;
+  const size_t g0 = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32;
+  const int in_range = (int)min((size_t)32, (size_t)a.P > g0 ? (size_t)a.P - g0 : (size_t)0);
+  if (a.M == 16) {
+    float4* dst = reinterpret_cast<float4*>(a.dL_dsh + g0 * 48);
+#pragma unroll 4
+    for (int i = lane; i < in_range * 12; i += 32) {
+      const int g = i / 12, j = (i - g * 12) * 4;
+      const float* r = &s_out[warp][g * SHV_ROW + j];
+      dst[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  } else {
+    for (int i = lane; i < in_range * row; i += 32) {
+      const int g = i / row, j = i - g * row;
+      a.dL_dsh[(g0 + g) * (size_t)row + j] = j < 48 ? s_out[warp][g * SHV_ROW + j] : 0.f;
+    }
+  }
+  (void)maxD;
+}
+
+}  // namespace
+
+extern "C" GOF_API int gof_sh_grad_from_views(int P, int M, int n_views, const float* means3D, const float* const* slots, float* dL_dsh,
+                                              void* stream) {
+  if (P < 0 || M < 1 || M > 16 || n_views < 1 || n_views > SHV_MAX_VIEWS || !slots) {
+    gof_set_error("sh_grad_from_views: bad arguments (1 <= M <= 16, 1 <= n_views <= %d)", SHV_MAX_VIEWS);
+    return GOF_E_INVALID;
+  }
+  if (P == 0) return GOF_OK;
+  if (!means3D || !dL_dsh || (reinterpret_cast<uintptr_t>(dL_dsh) & 15u)) { gof_set_error("sh_grad_from_views: NULL or unaligned argument"); return GOF_E_INVALID; }
+  ShvArgs a;
+  a.P = P; a.M = M; a.n_views = n_views; a.means3D = means3D; a.dL_dsh = dL_dsh;
+  for (int v = 0; v < SHV_MAX_VIEWS; ++v) a.slot[v] = v < n_views ? slots[v] : nullptr;
+  for (int v = 0; v < n_views; ++v)
+    if (!a.slot[v]) { gof_set_error("sh_grad_from_views: NULL view record"); return GOF_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  GOF_LAUNCH("sh_grad_from_views", st, k_sh_grad_from_views<<<(P + SHV_THREADS - 1) / SHV_THREADS, SHV_THREADS, 0, st>>>(a));
+  GOF_LAUNCH_CHECK(false, st);
+  return GOF_OK;
+}

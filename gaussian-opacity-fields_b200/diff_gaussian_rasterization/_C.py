@@ -55,6 +55,10 @@ _lib.gof_rasterize_backward.restype = ctypes.c_int
 _lib.gof_rasterize_backward.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int] + [_fp] * 15 + [ctypes.c_void_p]
 _lib.gof_rasterize_backward_stats.restype = ctypes.c_int
 _lib.gof_rasterize_backward_stats.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int] + [_fp] * 17 + [ctypes.c_void_p]
+_lib.gof_rasterize_backward_dp.restype = ctypes.c_int
+_lib.gof_rasterize_backward_dp.argtypes = [ctypes.POINTER(_Scene), ctypes.c_int] + [_fp] * 19 + [ctypes.c_void_p]
+_lib.gof_sh_grad_from_views.restype = ctypes.c_int
+_lib.gof_sh_grad_from_views.argtypes = [ctypes.c_int] * 3 + [_fp, ctypes.c_void_p, _fp, ctypes.c_void_p]
 _lib.gof_mark_visible.restype = ctypes.c_int
 _lib.gof_mark_visible.argtypes = [ctypes.c_int, _fp, _fp, _fp, _fp, ctypes.c_void_p]
 _lib.gof_integrate.restype = ctypes.c_int
@@ -252,7 +256,19 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     # contiguous, 256-byte aligned view of the block.
     shapes = dict(dmeans3D=(P, 3), dmeans2D=(P, 3), dcolors=(P, 3), dopacity=(P, 1), dcov3D=(P, 6), dsh=(P, M, 3),
                   dscales=(P, 3), drot=(P, 4), dv2g=(P, 10))
-    need = {k: v for k, v in shapes.items() if not (_out is not None and k in _out)}
+    # `_out` with "dsh_rgb" (P,3) + "sh_hdr" (>= 4 floats): the factored SH gradient of view-parallel training (gof_dp.GradBucket,
+    # csrc/sh_views.cu) -- the backward leaves the clamp-masked dL_dRGB and the camera centre instead of dL_dsh, which only exists
+    # after the bucket's exchange (the returned dL_dsh is then _out.get("dsh"): the tensor the exchange fills)
+    factored = _out is not None and "dsh_rgb" in _out
+    if factored:
+        rgb_t, hdr_t = _out["dsh_rgb"], _out.get("sh_hdr")
+        if sh is None or sh.numel() == 0:
+            raise RuntimeError("gof_b200: the factored SH gradient (_out['dsh_rgb']) needs SH input")
+        if hdr_t is None or not (rgb_t.is_contiguous() and hdr_t.is_contiguous() and tuple(rgb_t.shape) == (P, 3) and hdr_t.numel() >= 4
+                                 and rgb_t.dtype == torch.float32 and hdr_t.dtype == torch.float32):
+            raise RuntimeError("gof_b200: _out['dsh_rgb'] must be a contiguous float32 (P,3) tensor and _out['sh_hdr'] hold >= 4 floats")
+        _out["_means3D"] = means3D if means3D.is_contiguous() else means3D.contiguous()
+    need = {k: v for k, v in shapes.items() if not (_out is not None and k in _out) and not (factored and k == "dsh")}
     offs, total = {}, 0
     for k, shp in need.items():
         offs[k] = total
@@ -283,7 +299,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     dL_dconic = None       # the reference allocates (P,2,2) zeros that nothing writes or returns
     dL_dopacity = _z("dopacity", (P, 1))
     dL_dcov3D = _z("dcov3D", (P, 6))
-    dL_dsh = _z("dsh", (P, M, 3))
+    dL_dsh = _out.get("dsh") if factored else _z("dsh", (P, M, 3))
     dL_dscales = _z("dscales", (P, 3))
     dL_drotations = _z("drot", (P, 4))
     dL_dv2g = _z("dv2g", (P, 10))
@@ -299,13 +315,14 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             if ds is not None and not (ds.is_contiguous() and dm.is_contiguous() and tuple(ds.shape) == (P, 3) and tuple(dm.shape) == (P, 2)
                                        and ds.dtype == torch.float32 and dm.dtype == torch.float32):
                 raise RuntimeError("gof_b200: dens_sum must be a contiguous float32 (P,3) and dens_max (P,2) tensor")
-            _check(_lib.gof_rasterize_backward_stats(
+            _check(_lib.gof_rasterize_backward_dp(
                 ctypes.byref(s), int(R), _ptr(rad, torch.int32), _ptr(geomBuffer, torch.uint8),
                 _ptr(binningBuffer, torch.uint8), _ptr(imageBuffer, torch.uint8), _ptr(g),
                 dL_dmeans2D.data_ptr(), None, dL_dopacity.data_ptr(), dL_dcolors.data_ptr(),
-                dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), _ptr(dL_dsh), dL_dscales.data_ptr(),
+                dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), None if factored else _ptr(dL_dsh), dL_dscales.data_ptr(),
                 dL_drotations.data_ptr(), dL_dv2g.data_ptr(), ds.data_ptr() if ds is not None else None,
-                dm.data_ptr() if dm is not None else None, _stream()))
+                dm.data_ptr() if dm is not None else None, rgb_t.data_ptr() if factored else None,
+                hdr_t.data_ptr() if factored else None, _stream()))
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
             dL_dv2g)
 

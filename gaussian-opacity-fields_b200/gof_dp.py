@@ -14,6 +14,13 @@ into a torch symmetric-memory allocation (plumbing: it binds every rank's copy t
 it with the library's multimem kernel: the switch adds the ranks' copies (multimem.ld_reduce) and broadcasts the result
 (multimem.st) -- one bucket of NVLink traffic per GPU and direction instead of 2 (N-1)/N.
 
+Factored SH gradient (`GradBucket(..., factor_sh=True)`): 48 of the 59 gradient floats per Gaussian are dL_dsh, and ONE view's
+dL_dsh is an outer product w(dir(mean, camera)) (x) dL_dRGB (backward.cu:45-139).  Every rank holds all means, so the ranks only
+need each other's clamp-masked dL_dRGB -- 3 floats per Gaussian and view -- and each expands sum_v w(dir_v) (x) rgb_v itself
+(csrc/sh_views.cu), in rank order, bit-identical to adding the views' dL_dsh tensors.  The reduced part of the bucket shrinks from
+64 to 16 floats per Gaussian; the per-view records sit behind it ([world] x (64-float header + [P,3])) and are read in place over
+NVLink by the expansion kernel (peer-memory / NVLS exchange) or all-gathered (NCCL / gloo).
+
 The bucket also carries this view's densification statistics (written by the rasterizer backward itself, see
 gof_rasterize_backward_stats): `dens_sum` (P,3) = (|dL_dmean2D.xy|, |dL_dmean2D.z|, visible) reduced with SUM and `dens_max`
 (P,2) = (|dL_dmean2D.z|, radius) reduced with MAX -- what GaussianModel.add_densification_stats and train.py:255 accumulate.
@@ -26,16 +33,29 @@ import torch.distributed as dist
 # per-Gaussian parameter gradients that must be reduced across views: 3 + 48 + 1 + 3 + 4 = 59 floats
 _FIELDS = (("dmeans3D", (3,)), ("dsh", None), ("dopacity", (1,)), ("dscales", (3,)), ("drot", (4,)))
 _STAT_FIELDS = (("dens_sum", (3,)), ("dens_max", (2,)))       # SUM region ends where dens_max starts
+SH_SLOT_HEADER = 64                                           # floats in front of a view record's rgb (include/gof_rasterizer.h)
 
 
 class GradBucket:
     """Flat fp32 buffer [sum of fields] with one contiguous, correctly shaped view per gradient tensor."""
 
-    def __init__(self, P, M, device, dtype=torch.float32, with_stats=True, extra_sum=0):
-        """`extra_sum`: additional floats summed with the gradients (view "extra": e.g. the appearance network's gradients)."""
+    def __init__(self, P, M, device, dtype=torch.float32, with_stats=True, extra_sum=0, factor_sh=False, group=None):
+        """`extra_sum`: additional floats summed with the gradients (view "extra": e.g. the appearance network's gradients).
+        `factor_sh`: exchange dL_dRGB per view instead of dL_dsh (module docstring); needs an initialised process group (the
+        number of view records is its world size).  views["dsh"] is then a local tensor that all_reduce() fills, and the
+        rasterizer backward is handed views["dsh_rgb"] / views["sh_hdr"] (it finds them in `_out=bucket.views`)."""
         self.P, self.M = int(P), int(M)
+        self.factored = bool(factor_sh)
+        if self.factored:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("GradBucket(factor_sh=True) needs an initialised process group")
+            self._n_views, self._view = dist.get_world_size(group), dist.get_rank(group)
+            if self._n_views > 16:
+                raise RuntimeError("GradBucket(factor_sh=True): at most 16 ranks (csrc/sh_views.cu)")
         shapes = {}
         for name, tail in _FIELDS:
+            if name == "dsh" and self.factored:
+                continue
             shapes[name] = (self.P, self.M, 3) if name == "dsh" else (self.P,) + tail
         if extra_sum:
             shapes["extra"] = (int(extra_sum),)
@@ -48,8 +68,15 @@ class GradBucket:
         for name, shape in shapes.items():
             self._offsets[name] = (off, shape)
             off += (int(torch.Size(shape).numel()) + 63) // 64 * 64
+        self.n_reduce = off                                                    # floats [0, n_reduce) are reduced over the ranks:
+        self.n_sum = self._offsets["dens_max"][0] if with_stats else off      #   [0, n_sum) SUM, [n_sum, n_reduce) MAX
+        self._slot = 0
+        self.dsh = None
+        if self.factored:    # [n_reduce, numel): one record per view = SH_SLOT_HEADER floats (camera centre, degree) + rgb [P,3]
+            self._slot = SH_SLOT_HEADER + (self.P * 3 + 63) // 64 * 64
+            off += self._n_views * self._slot
+            self.dsh = torch.zeros(self.P, self.M, 3, dtype=dtype, device=device)
         self.numel = off
-        self.n_sum = self._offsets["dens_max"][0] if with_stats else off      # floats [0, n_sum): SUM, [n_sum, numel): MAX
         self.flat = torch.zeros(max(self.numel, 64), dtype=dtype, device=device)
         self.views = self._make_views()
         self._symm = None        # torch symmetric-memory handle (NVLS exchange)
@@ -60,10 +87,58 @@ class GradBucket:
         self.exchange = "nccl"
 
     def _make_views(self):
-        return {name: self.flat[off:off + int(torch.Size(shape).numel())].view(shape) for name, (off, shape) in self._offsets.items()}
+        views = {name: self.flat[off:off + int(torch.Size(shape).numel())].view(shape) for name, (off, shape) in self._offsets.items()}
+        if self.factored:
+            rec = self._record(self._view)
+            views["sh_hdr"] = rec[:SH_SLOT_HEADER]
+            views["dsh_rgb"] = rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P].view(self.P, 3)
+            views["dsh"] = self.dsh
+        return views
+
+    def _record(self, v):
+        """View v's record inside THIS rank's buffer (valid for v != own rank only after an all-gather)."""
+        return self.flat[self.n_reduce + v * self._slot:self.n_reduce + (v + 1) * self._slot]
 
     def zero_(self):
         self.flat.zero_()
+        if self.dsh is not None:
+            self.dsh.zero_()
+
+    # ---- factored SH gradient: sum over the views' records ------------------------------------------------------
+    def _expand_sh(self, record_ptrs, means3D):
+        """dsh = sum_v w(dir(means3D, camera_v)) (x) rgb_v from the records at `record_ptrs` (device addresses valid in this
+        process: local or peer memory), by the library's kernel."""
+        from diff_gaussian_rasterization import _C
+        if means3D is None:
+            means3D = self.views.get("_means3D")
+        if means3D is None:
+            raise RuntimeError("GradBucket.all_reduce: the factored SH gradient needs means3D (run the rasterizer backward with _out=bucket.views "
+                               "first, or pass means3D=)")
+        if not (means3D.is_cuda and means3D.dtype == torch.float32 and means3D.is_contiguous() and tuple(means3D.shape) == (self.P, 3)):
+            raise RuntimeError("GradBucket: means3D must be a contiguous CUDA float32 (P,3) tensor")
+        arr = (ctypes.c_void_p * len(record_ptrs))(*record_ptrs)
+        with torch.cuda.device(self.flat.device):
+            _C._check(_C._lib.gof_sh_grad_from_views(self.P, self.M, len(record_ptrs), means3D.data_ptr(), arr, self.dsh.data_ptr(), _C._stream()))
+
+    def _expand_sh_torch(self, means3D):
+        """The same sum with torch ops from the all-gathered local records (CPU buckets of the gloo tests; the reference the CUDA
+        kernel is tested against)."""
+        if means3D is None:
+            means3D = self.views.get("_means3D")
+        if means3D is None:
+            raise RuntimeError("GradBucket.all_reduce: the factored SH gradient needs means3D")
+        self.dsh.copy_(sh_grad_from_views_torch(means3D, [self._record(v) for v in range(self._n_views)], self.P, self.M))
+
+    def _record_ptrs(self):
+        """Addresses (valid in this process) of every rank's record IN THAT RANK'S OWN BUFFER, or None when peers' memory is
+        not mapped (NCCL / gloo: the records are all-gathered into the local buffer instead)."""
+        tail = lambda r: 4 * (self.n_reduce + r * self._slot)   # noqa: E731
+        if self.exchange == "p2p":
+            return [int(self._peer_ptrs[r]) + tail(r) for r in range(self._n_views)]
+        if self.exchange == "nvls":
+            off = self.flat.data_ptr() - int(self._symm.buffer_ptrs[self._view])
+            return [int(self._symm.buffer_ptrs[r]) + off + tail(r) for r in range(self._n_views)]
+        return None
 
     def enable_peer_exchange(self, group=None):
         """Move the bucket into a CUDA-IPC shareable allocation, map every other rank's bucket into this process (one node,
@@ -134,9 +209,10 @@ class GradBucket:
         dist.barrier(group=group)
         # self-test on the live mapping: ones must sum to `world` in every bucket
         self.flat.fill_(1.0)
-        self.all_reduce(group=group)
+        self.all_reduce(group=group, _expand=False)
         torch.cuda.synchronize(dev)
-        good = agree(bool((self.flat[:self.n_sum] == float(world)).all().item()) and bool((self.flat[self.n_sum:] == 1.0).all().item()))
+        good = bool((self.flat[:self.n_sum] == float(world)).all().item()) and bool((self.flat[self.n_sum:self.n_reduce] == 1.0).all().item())
+        good = agree(good and self._selftest_records(group))
         self.flat.zero_()
         if not good:
             self.close()
@@ -235,11 +311,11 @@ class GradBucket:
         # self-test on the live mapping: rank r contributes r+1 to the SUM part and r to the MAX tail
         self.flat[:self.n_sum].fill_(float(rank + 1))
         self.flat[self.n_sum:].fill_(float(rank))
-        self.all_reduce(group=group)
+        self.all_reduce(group=group, _expand=False)
         torch.cuda.synchronize(dev)
         good = bool((self.flat[:self.n_sum] == float(world * (world + 1) // 2)).all().item()) and \
-            bool((self.flat[self.n_sum:] == float(world - 1)).all().item())
-        good = agree(good)
+            bool((self.flat[self.n_sum:self.n_reduce] == float(world - 1)).all().item())
+        good = agree(good and self._selftest_records(group))
         self.flat.zero_()
         if not good:
             self.flat, self.views, self.exchange = old
@@ -289,10 +365,41 @@ class GradBucket:
         self.flat.zero_()
         return report
 
-    def all_reduce(self, group=None, async_op=False):
-        """SUM over ranks of floats [0, n_sum), MAX of the statistics tail [n_sum, numel).  World size 1: no-op."""
+    def _selftest_records(self, group=None):
+        """Factored bucket, peer-memory / NVLS mode: the expansion kernel reading the peers' records in place gives what torch
+        computes from an NCCL all-gather of the same records.  Collective; True when not factored."""
+        if not self.factored:
+            return True
+        dev, rank = self.flat.device, self._view
+        gen = torch.Generator().manual_seed(1234)
+        means = (torch.rand(self.P, 3, generator=gen) * 4 - 2).to(dev)
+        rec = self._record(rank)
+        rec.zero_()
+        rec[:4] = torch.tensor([0.3 * rank - 0.5, 0.25, -3.0 - 0.1 * rank, 3.0], device=dev)
+        rgb = torch.randn(self.P, 3, generator=torch.Generator().manual_seed(77 + rank)).to(dev)
+        rgb[rank::5] = 0.0
+        rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P] = rgb.reshape(-1)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        self._expand_sh(self._record_ptrs(), means)
+        got = self.dsh.clone()
+        recs = [torch.empty_like(rec) for _ in range(self._n_views)]
+        dist.all_gather(recs, rec.clone(), group=group)
+        want = sh_grad_from_views_torch(means, recs, self.P, self.M)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        self.dsh.zero_()
+        return bool(torch.allclose(got, want, rtol=1e-4, atol=1e-5))
+
+    def all_reduce(self, group=None, async_op=False, means3D=None, _expand=True):
+        """SUM over ranks of floats [0, n_sum), MAX of the statistics tail [n_sum, n_reduce); a factored bucket then fills
+        views["dsh"] with the sum over all ranks' views (`means3D`: the Gaussian centres the backward ran on -- remembered from
+        the last rasterizer backward into this bucket when not given).  World size 1: no-op."""
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
+        expand = self.factored and _expand
+        if async_op and expand:
+            raise ValueError("GradBucket.all_reduce(async_op=True) is not available for a factored bucket (the SH expansion follows the exchange)")
         if self.exchange in ("p2p", "nvls"):
             if async_op:
                 raise ValueError("GradBucket.all_reduce(async_op=True) is not available with the peer-memory / NVLS exchange: "
@@ -303,22 +410,72 @@ class GradBucket:
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             with torch.cuda.device(self.flat.device):
                 if self.exchange == "p2p":
-                    self._check(self._lib.gof_p2p_allreduce_f32(self._peer_ptrs, self._world, self._rank, self.n_sum, self.flat.numel(), stream))
+                    self._check(self._lib.gof_p2p_allreduce_f32(self._peer_ptrs, self._world, self._rank, self.n_sum, self.n_reduce, stream))
                 else:
                     self._check(self._lib.gof_nvls_allreduce_f32(ctypes.c_void_p(self._mc), self._world, self._rank, self.n_sum,
-                                                                 self.flat.numel(), stream))
-            # barrier: every slice has been written into every bucket
+                                                                 self.n_reduce, stream))
+            if expand:   # the views' records are read where the ranks left them, over NVLink
+                self._expand_sh(self._record_ptrs(), means3D)
+            # barrier: every slice has been written into every bucket (and every record has been read)
             dist.all_reduce(self._sync, group=group)
             return None
         if self.n_sum == self.flat.numel():
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         w1 = dist.all_reduce(self.flat[:self.n_sum], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-        w2 = dist.all_reduce(self.flat[self.n_sum:], op=dist.ReduceOp.MAX, group=group, async_op=async_op)
+        w2 = None
+        if self.n_reduce > self.n_sum:
+            w2 = dist.all_reduce(self.flat[self.n_sum:self.n_reduce], op=dist.ReduceOp.MAX, group=group, async_op=async_op)
+        if expand:
+            own = self._record(self._view)
+            if self.flat.is_cuda:
+                dist.all_gather_into_tensor(self.flat[self.n_reduce:], own, group=group)     # in place: own record already sits at its slot
+                self._expand_sh([self.flat.data_ptr() + 4 * (self.n_reduce + v * self._slot) for v in range(self._n_views)], means3D)
+            else:
+                recs = [torch.empty_like(own) for _ in range(self._n_views)]
+                dist.all_gather(recs, own.clone(), group=group)
+                for v, r in enumerate(recs):
+                    self._record(v).copy_(r)
+                self._expand_sh_torch(means3D)
         return (w1, w2) if async_op else None
 
     @property
     def nbytes(self):
+        """Bytes of the exchanged buffer (reduced part + the views' records)."""
         return self.flat.numel() * self.flat.element_size()
+
+
+_SH_C1 = 0.4886025119029199
+_SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+_SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658, 1.445305721320277,
+          -0.5900435899266435)
+
+
+def sh_grad_weights_torch(dirs, degree):
+    """d colour / d SH coefficient for unit directions `dirs` [P,3]: [P,(degree+1)^2] (backward.cu:45-139; gof_sh_grad_weights)."""
+    x, y, z = dirs[:, 0], dirs[:, 1], dirs[:, 2]
+    w = [torch.full_like(x, 0.28209479177387814)]
+    if degree > 0:
+        w += [-_SH_C1 * y, _SH_C1 * z, -_SH_C1 * x]
+    if degree > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        w += [_SH_C2[0] * xy, _SH_C2[1] * yz, _SH_C2[2] * (2 * zz - xx - yy), _SH_C2[3] * xz, _SH_C2[4] * (xx - yy)]
+    if degree > 2:
+        w += [_SH_C3[0] * y * (3 * xx - yy), _SH_C3[1] * xy * z, _SH_C3[2] * y * (4 * zz - xx - yy), _SH_C3[3] * z * (2 * zz - 3 * xx - 3 * yy),
+              _SH_C3[4] * x * (4 * zz - xx - yy), _SH_C3[5] * z * (xx - yy), _SH_C3[6] * x * (xx - 3 * yy)]
+    return torch.stack(w, dim=1)
+
+
+def sh_grad_from_views_torch(means3D, records, P, M):
+    """sum_v w(dir(means3D, camera_v)) (x) rgb_v as [P,M,3] from view records (header: camera centre, degree | rgb [P,3])."""
+    out = torch.zeros(P, M, 3, dtype=means3D.dtype, device=means3D.device)
+    for rec in records:
+        cam, degree = rec[:3], int(round(float(rec[3])))
+        rgb = rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * P].view(P, 3)
+        d = means3D - cam[None, :]
+        d = d / torch.linalg.vector_norm(d, dim=1, keepdim=True)
+        w = sh_grad_weights_torch(d, degree)
+        out[:, :w.shape[1], :] += w[:, :, None] * rgb[:, None, :]
+    return out
 
 
 def densification_stats(dmeans2D, radii):

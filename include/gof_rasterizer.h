@@ -105,13 +105,32 @@ GOF_API int gof_rasterize_backward(const gof_scene_t* scene, int num_rendered, c
 /* gof_rasterize_backward that also leaves this view's densification statistics next to the gradients (view-parallel training
  * reduces them in the same exchange): dens_sum [P,3] = (|dL_dmean2D.xy|, |dL_dmean2D.z|, 1) and dens_max [P,2] =
  * (|dL_dmean2D.z|, radius) for visible Gaussians -- what GaussianModel.add_densification_stats (scene/gaussian_model.py:709-714)
- * and train.py:255 accumulate per view with SUM resp. MAX.  Rows of invisible Gaussians are left untouched (pre-zero them).
- * Both NULL: plain gof_rasterize_backward. */
+ * and train.py:255 accumulate per view with SUM resp. MAX.  Rows of invisible Gaussians are written as zeros (like every
+ * gradient output: no pre-zeroing needed).  Both NULL: plain gof_rasterize_backward. */
 GOF_API int gof_rasterize_backward_stats(const gof_scene_t* scene, int num_rendered, const int* radii, void* geom_buffer,
                            const void* binning_buffer, const void* image_buffer, const float* dL_dpix, float* dL_dmean2D,
                            float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
                            float* dL_dsh, float* dL_dscale, float* dL_drot, float* dL_dview2gaussian, float* dens_sum,
                            float* dens_max, void* stream);
+
+/* View-parallel training (one view per GPU, gradients summed over the GPUs; no reference counterpart -- the reference is
+ * single-GPU).  The SH gradient of ONE view is an outer product: dL_dsh[g][k][c] = w_k(dir(mean_g, camera)) * dL_dRGB[g][c]
+ * (backward.cu:45-139), so the ranks exchange the 3 floats of the clamp-masked dL_dRGB per Gaussian and view instead of the
+ * 48 of dL_dsh and every rank expands the sum over the views itself (gof_sh_grad_from_views).
+ * gof_rasterize_backward_dp = gof_rasterize_backward_stats that additionally writes sh_rgb [P,3] (zeros for invisible
+ * Gaussians) and sh_hdr[0..3] = camera centre, active SH degree; with both given dL_dsh may be NULL (it is then not computed). */
+GOF_API int gof_rasterize_backward_dp(const gof_scene_t* scene, int num_rendered, const int* radii, void* geom_buffer,
+                           const void* binning_buffer, const void* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+                           float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                           float* dL_dsh, float* dL_dscale, float* dL_drot, float* dL_dview2gaussian, float* dens_sum,
+                           float* dens_max, float* sh_rgb, float* sh_hdr, void* stream);
+/* dL_dsh [P,M,3] = sum over v = 0..n_views-1, in that order, of w(dir(means3D, camera_v)) (x) rgb_v, bit-identical to adding the
+ * views' own dL_dsh in that order; coefficients above the active degree are written as zeros.  slots[v] points to view v's
+ * record: 64 floats of header (sh_hdr as written by gof_rasterize_backward_dp) followed by rgb [P,3]; the pointers may address
+ * peer GPUs' memory (NVLink): the records are then read where the ranks left them, without a gather step. */
+#define GOF_SH_SLOT_HEADER 64
+GOF_API int gof_sh_grad_from_views(int P, int M, int n_views, const float* means3D, const float* const* slots, float* dL_dsh,
+                           void* stream);
 
 /* Rasterizer::integrate (rasterizer_impl.cu:530-792) == _C.integrate_gaussians_to_points.
  * out_alpha_integrated [PN] must be initialised to 1 and out_color_integrated [PN,3] to 0 by the
