@@ -194,13 +194,16 @@ E2E_API = ("GaussianRasterizer.forward + autograd backward + L1/normal/depth/dis
            "slot one step late -- the SAME harness (bench.run_e2e_harness) drives both arms")
 
 
-def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls, app=None):
+def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls, app=None, bucket=None):
     """End-to-end steps through a package's public drop-in API (`GaussianRasterizer(settings)(...)` + autograd), used
     unchanged for this repo's package and for the reference's own package (--impl reference), so that the two `e2e`
     numbers differ only in the rasterizer.  Input pipeline as a training loop runs it: this step's camera + ground-truth
     image travel from pinned host memory on a copy stream into one of two device buffers while the previous step computes;
     the loss goes back through a pinned slot and is read by the host one step later.  Every copy is issued, and completes,
-    inside the timed region.  Returns (milliseconds for args.steps steps, max over ranks; H2D bytes per step)."""
+    inside the timed region.  Returns (milliseconds for args.steps steps, max over ranks; H2D bytes per step).
+    N > 1: the per-Gaussian gradients are summed over the ranks every step -- by one NCCL all-reduce of the concatenated .grad
+    tensors, or, when the package offers it (`bucket`: this repo's gof_dp.GradBucket, handed to its GaussianRasterizer), by the
+    package's own exchange."""
     params = {k: wl.gs[k].detach().clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
     h2d = wl.cam_host[0].numel() * 4 + wl.gt_host.numel() * 4
     copy_stream = torch.cuda.Stream()
@@ -235,7 +238,8 @@ def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls, app=None
         means2D = torch.zeros_like(params["means3D"], requires_grad=True)
         for p in params.values():
             p.grad = None
-        img, radii = rasterizer_cls(rs)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
+        rasterizer = rasterizer_cls(rs) if bucket is None else rasterizer_cls(rs, grad_bucket=bucket)
+        img, radii = rasterizer(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
                                         shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
         l_rgb = app.loss(img[:3], gt_buf[b], wl.view(step)) if app is not None else (img[:3] - gt_buf[b]).abs().mean()
         loss = l_rgb + 0.05 * (img[3:6] ** 2).mean() + 0.01 * img[6].mean() + 100.0 * img[8].mean()
@@ -245,7 +249,11 @@ def run_e2e_harness(args, wl, world, dev, rasterizer_cls, settings_cls, app=None
             app.emb.grad = None
         loss.backward()
         consumed[b].record(main)
-        if world > 1:
+        if world > 1 and bucket is not None:
+            if app is not None:
+                torch.cat([p.grad.flatten() for p in app.params] + [app.emb.grad[wl.view(step)]], out=bucket.views["extra"])
+            bucket.all_reduce()
+        elif world > 1:
             flat = torch.cat([params[k].grad.flatten() for k in ("means3D", "shs", "opacities", "scales", "rotations")] +
                              ([p.grad.flatten() for p in app.params] + [app.emb.grad[wl.view(step)]] if app is not None else []))
             dist.all_reduce(flat)
@@ -338,7 +346,10 @@ def run_ours(args, rank, world, dev):
 
     wl = Workload(args.config, dev, rank, world)
     app = AppearanceStep(wl, dev, "ours") if wl.cfg.get("appearance") else None
-    bucket = gof_dp.GradBucket(wl.P, 16, dev, extra_sum=app.numel if app else 0)
+    # N > 1: the SH gradient travels factored (3 floats of dL_dRGB per Gaussian and view instead of 48 of dL_dsh, expanded on
+    # every rank by csrc/sh_views.cu) unless --no-factor-sh asks for the plain 64-float bucket
+    factored = world > 1 and not args.no_factor_sh
+    bucket = gof_dp.GradBucket(wl.P, 16, dev, extra_sum=app.numel if app else 0, factor_sh=factored)
     exchange_note = None
     exchange_tuning = None
     if world > 1 and args.exchange == "auto":
@@ -369,27 +380,37 @@ def run_ours(args, rank, world, dev):
         step_device(s)
     exchange_check = None
     if world > 1:   # untimed: the exchanged bucket equals the combination of the per-rank single-GPU results
+        # every rank's OWN gradients from a plain single-GPU backward into an unfactored local bucket (full dL_dsh) ...
         fa = wl.fwd_args(wl.view(0))
         R0, _c0, radii0, geom0, bin0, img0 = _C.rasterize_gaussians(*fa)
+        single = gof_dp.GradBucket(wl.P, 16, dev)
+        _C.rasterize_gaussians_backward(*bwd_args(fa, radii0, geom0, R0, bin0, img0, wl.dL), _out=single.views)
+        # ... against the same backward into the exchanged bucket
         bucket.zero_()
         _C.rasterize_gaussians_backward(*bwd_args(fa, radii0, geom0, R0, bin0, img0, wl.dL), _out=bucket.views)
-        local = bucket.flat.clone()
-        parts = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(parts, local)
         bucket.all_reduce()
-        ns = bucket.n_sum
-        want_sum = torch.stack([p[:ns] for p in parts]).double().sum(0)
-        mag = torch.stack([p[:ns] for p in parts]).double().abs().sum(0)
-        want_max = torch.stack([p[ns:] for p in parts]).amax(0)
-        err = float(((bucket.flat[:ns].double() - want_sum).abs() / (1e-6 * mag + 1e-30)).max())      # <= 1: within 1e-6 of the magnitude sum
-        ok_sum, ok_max = err <= 1.0, bool(torch.equal(bucket.flat[ns:], want_max))
-        same = torch.tensor([float(bucket.flat.double().sum())], dtype=torch.float64, device=dev)
+        err, ok_max = 0.0, True
+        for name in ("dmeans3D", "dsh", "dopacity", "dscales", "drot", "dens_sum", "dens_max"):
+            mine = single.views[name].contiguous()
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            got = bucket.views[name]
+            if name == "dens_max":
+                ok_max = bool(torch.equal(got, torch.stack(parts).amax(0)))
+            else:
+                st = torch.stack(parts).double()
+                want, mag = st.sum(0), st.abs().sum(0)
+                err = max(err, float(((got.double() - want).abs() / (1e-6 * mag + 1e-30)).max()))      # <= 1: within 1e-6 of the magnitude sum
+            del parts
+        ok_sum = err <= 1.0
+        same = torch.tensor([float(bucket.flat[:bucket.n_reduce].double().sum()) + float(bucket.views["dsh"].double().sum())],
+                            dtype=torch.float64, device=dev)
         lo, hi = same.clone(), same.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         flag = torch.tensor([1.0 if (ok_sum and ok_max and float(lo) == float(hi)) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         exchange_check = "ok" if float(flag.item()) == 1.0 else f"FAILED (sum err {err:.3g}, max ok {ok_max}, identical on ranks {float(lo) == float(hi)})"
-        del parts, local, want_sum, mag, want_max, geom0, bin0, img0
+        del single, geom0, bin0, img0
     barrier_sync(world)
     launches0 = _C.launch_count()
     sampler = ClockSampler(torch.cuda.current_device())
@@ -431,7 +452,8 @@ def run_ours(args, rank, world, dev):
     del geom_s, bin_s, img_s
 
     # ---- end to end through the public API with host inputs (the same harness times the reference arm) --------
-    e2e_ms, h2d = run_e2e_harness(args, wl, world, dev, GaussianRasterizer, GaussianRasterizationSettings, app)
+    e2e_ms, h2d = run_e2e_harness(args, wl, world, dev, GaussianRasterizer, GaussianRasterizationSettings, app,
+                                  bucket=bucket if world > 1 else None)
 
     # the exchange step alone (N > 1): one all-reduce of the 59-float/Gaussian gradient bucket, CUDA events, max over ranks
     allreduce_ms = None
@@ -486,11 +508,15 @@ def run_ours(args, rank, world, dev):
                               "what": "AppearanceNetwork(67,3) forward + backward on the 1056x1920 crop and L1 (gof_appearance, torch/cuDNN convolutions, "
                                       "TF32 like the reference's default), CUDA events, inside the step"}
     if allreduce_ms is not None:
-        what = {"p2p": "59 gradient + 5 statistics f32 per Gaussian by the library's kernel over NVLink peer memory (csrc/exchange.cu), two NCCL barriers",
-                "nvls": "59 gradient + 5 statistics f32 per Gaussian reduced inside the NVSwitch by the library's multimem kernel "
-                        "(csrc/exchange.cu: multimem.ld_reduce + multimem.st on a symmetric-memory bucket), two NCCL barriers",
-                "nccl": "all-reduce(SUM) of 59 gradient + 3 statistics f32 per Gaussian and all-reduce(MAX) of 2 (NCCL)"}[bucket.exchange]
-        line["exchange"] = {"impl": bucket.exchange, "what": what, "bytes": int(bucket.nbytes), "ms": allreduce_ms}
+        per = "11 gradient + 5 statistics f32 per Gaussian reduced, 3 f32 of dL_dRGB per Gaussian and view exchanged as records and expanded to " \
+              "dL_dsh (48 f32) on every rank by csrc/sh_views.cu" if bucket.factored else "59 gradient + 5 statistics f32 per Gaussian"
+        what = {"p2p": per + "; reduction by the library's kernel over NVLink peer memory (csrc/exchange.cu), records read in place from the "
+                       "peers' buckets, two NCCL barriers",
+                "nvls": per + "; reduction inside the NVSwitch by the library's multimem kernel (csrc/exchange.cu: multimem.ld_reduce + "
+                        "multimem.st on a symmetric-memory bucket), records read in place from the peers' buckets, two NCCL barriers",
+                "nccl": per + "; NCCL all-reduce(SUM), all-reduce(MAX)" + (" and all-gather of the records" if bucket.factored else "")}[bucket.exchange]
+        line["exchange"] = {"impl": bucket.exchange, "what": what, "bytes": int(bucket.nbytes), "factored_sh": bool(bucket.factored),
+                            "ms": allreduce_ms}
         line["exchange_check"] = exchange_check
         if exchange_tuning:
             line["exchange"]["autotune_ms"] = exchange_tuning
@@ -1111,6 +1137,8 @@ def main():
                     help="N>1 gradient exchange: the library's multimem kernel through the NVSwitch (nvls), its NVLink peer-memory kernel "
                          "(p2p), NCCL's all-reduce (nccl), or auto = nvls, else p2p, else nccl -- each mode is adopted only after a "
                          "collective self-test on the live mapping")
+    ap.add_argument("--no-factor-sh", action="store_true", help="N>1: exchange the full dL_dsh (64 floats per Gaussian in the bucket) instead of "
+                                                               "the per-view dL_dRGB records (16 reduced + 3 per view)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():

@@ -44,14 +44,14 @@ def _to_cpu(args):
     return tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
 
 
-def _call_native(fn, args, debug, dump_name, what):
+def _call_native(fn, args, debug, dump_name, what, **kw):
     """Calls a `_C` entry point; with debug the inputs are snapshotted first and written to
     `dump_name` if the native call raises (reference :89-96, :141-148, :292-301)."""
     if not debug:
-        return fn(*args)
+        return fn(*args, **kw)
     snapshot = _to_cpu(args)
     try:
-        return fn(*args)
+        return fn(*args, **kw)
     except Exception:
         torch.save(snapshot, dump_name)
         print(f"\nAn error occured in {what}. Please forward {dump_name} for debugging.")
@@ -65,8 +65,9 @@ def _camera_args(rs):
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                view2gaussian_precomp, raster_settings):
+                view2gaussian_precomp, raster_settings, grad_bucket=None):
         rs = raster_settings
+        ctx.grad_bucket = grad_bucket
         args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 view2gaussian_precomp) + _camera_args(rs) + (rs.image_height, rs.image_width, sh, rs.sh_degree,
                                                              rs.campos, rs.prefiltered, rs.debug)
@@ -87,16 +88,23 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 view2gaussian_precomp) + _camera_args(rs) + (grad_out_color, sh, rs.sh_degree, rs.campos, geom,
                                                              ctx.num_rendered, binning, img, rs.debug)
+        bucket = ctx.grad_bucket
         (g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot, g_v2g) = _call_native(
-            _C.rasterize_gaussians_backward, args, rs.debug, "snapshot_bw.dump", "backward")
+            _C.rasterize_gaussians_backward, args, rs.debug, "snapshot_bw.dump", "backward",
+            **({"_out": bucket.views} if bucket is not None else {}))
+        if bucket is not None:
+            # extension (view-parallel training, gof_dp.GradBucket): the parameter gradients and this view's densification
+            # statistics were written INTO the bucket -- they are read from bucket.views after bucket.all_reduce(), not from
+            # .grad (autograd would copy the 256 MB out of the exchange buffer again)
+            g_means3D = g_sh = g_opacity = g_scales = g_rot = None
         # one gradient per forward input, in input order (reference :152-163)
-        return (g_means3D, g_means2D, g_sh, g_colors, g_opacity, g_scales, g_rot, g_cov3D, g_v2g, None)
+        return (g_means3D, g_means2D, g_sh, g_colors, g_opacity, g_scales, g_rot, g_cov3D, g_v2g, None, None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         view2gaussian_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, view2gaussian_precomp, raster_settings)
+                                     cov3Ds_precomp, view2gaussian_precomp, raster_settings, None)
 
 
 def _absent():
@@ -117,9 +125,13 @@ def _normalise_optionals(shs, colors_precomp, scales, rotations, cov3D_precomp, 
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings):
+    def __init__(self, raster_settings, grad_bucket=None):
+        """`grad_bucket` (extension, not in the reference): a gof_dp.GradBucket -- the backward then writes the gradients of
+        means3D / shs / opacities / scales / rotations and the view's densification statistics into the bucket (the buffer a
+        view-parallel step exchanges) instead of returning them to autograd."""
         super().__init__()
         self.raster_settings = raster_settings
+        self.grad_bucket = grad_bucket
 
     def markVisible(self, positions):
         """bool[P]: view-space z > 0.2 (rasterizer_impl.cu:54-66)."""
@@ -131,6 +143,9 @@ class GaussianRasterizer(nn.Module):
                 cov3D_precomp=None, view2gaussian_precomp=None):
         shs, colors_precomp, scales, rotations, cov3D_precomp, view2gaussian_precomp = _normalise_optionals(
             shs, colors_precomp, scales, rotations, cov3D_precomp, view2gaussian_precomp)
+        if self.grad_bucket is not None:
+            return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                             cov3D_precomp, view2gaussian_precomp, self.raster_settings, self.grad_bucket)
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
                                    cov3D_precomp, view2gaussian_precomp, self.raster_settings)
 

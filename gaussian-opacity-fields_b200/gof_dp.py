@@ -333,6 +333,17 @@ class GradBucket:
             return {}
         dev = self.flat.device
         report, best, best_ms = {}, "nccl", float("inf")
+        means = None
+        if self.factored:     # realistic records: the expansion kernel skips Gaussians whose dL_dRGB is zero
+            means = (torch.rand(self.P, 3, generator=torch.Generator().manual_seed(1)) * 4 - 2).to(dev)
+
+        def prime():
+            if self.factored:
+                rec = self._record(self._view)
+                rec[:4] = torch.tensor([0.3 * self._view - 0.5, 0.25, -3.0, 3.0], device=dev)
+                rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P].normal_()
+                rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P:7] = 0.0
+                self.views["_means3D"] = means
         for mode in modes:
             try:
                 if mode == "nvls":
@@ -342,6 +353,7 @@ class GradBucket:
             except Exception as e:   # noqa: BLE001 -- symmetric on all ranks
                 report[mode] = f"unavailable ({type(e).__name__}: {str(e)[:120]})"
                 continue
+            prime()
             for _ in range(2):
                 self.all_reduce(group=group)
             dist.barrier(group=group)
@@ -362,7 +374,7 @@ class GradBucket:
             self.enable_nvls_exchange(group)
         elif best == "p2p":
             self.enable_peer_exchange(group)
-        self.flat.zero_()
+        self.zero_()
         return report
 
     def _selftest_records(self, group=None):

@@ -104,3 +104,86 @@ def test_bucket_layout_and_padding():
         assert b.enable_peer_exchange() is b and b.exchange == "nccl"
         assert b.all_reduce() is None
         b.close()                                   # no-op outside peer mode
+
+
+def _worker_factored(rank, world, port, q):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "..", "gaussian-opacity-fields_b200"))
+    import gof_dp
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, M = 203, 16
+    b = gof_dp.GradBucket(P, M, "cpu", factor_sh=True)
+    assert "dsh_rgb" in b.views and b.views["dsh"].shape == (P, M, 3) and b.n_reduce == b.n_sum + 2 * P // 64 * 64 + 64 * (2 * P % 64 != 0)
+    assert b.numel == b.n_reduce + world * (64 + (3 * P + 63) // 64 * 64)
+    g = torch.Generator().manual_seed(10 + rank)
+    means = torch.randn(P, 3, generator=torch.Generator().manual_seed(5)) * 2     # the same Gaussians on every rank
+    cam = torch.tensor([3.0 + rank, -1.0, 0.5 * rank])
+    degree = 3 - rank                                                             # (ranks may be at different degrees only in a test)
+    local = {}
+    for name in ("dmeans3D", "dopacity", "dscales", "drot", "dens_sum", "dens_max", "dsh_rgb"):
+        b.views[name].copy_(torch.randn(b.views[name].shape, generator=g))
+        local[name] = b.views[name].clone()
+    b.views["dsh_rgb"][::3] = 0.0
+    local["dsh_rgb"] = b.views["dsh_rgb"].clone()
+    b.views["sh_hdr"][:4] = torch.tensor([cam[0], cam[1], cam[2], float(degree)])
+    b.all_reduce(means3D=means)
+    q.put((rank, {k: v.numpy().copy() for k, v in local.items()}, {k: v.numpy().copy() for k, v in b.views.items()},
+           means.numpy().copy(), cam.numpy().copy(), degree))
+    dist.destroy_process_group()
+
+
+def test_factored_sh_bucket_world2():
+    """GradBucket(factor_sh=True) over gloo: the reduced fields are the sums / maxima, and views['dsh'] is the sum over the
+    ranks of the outer products w(dir(mean, camera_r)) (x) rgb_r -- checked against an independent evaluation of the reference's
+    SH backward (computeColorFromSH's gradient through autograd of the forward polynomial)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_factored, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t = lambda a: torch.from_numpy(a)   # noqa: E731
+    for name in ("dmeans3D", "dopacity", "dscales", "drot", "dens_sum", "dens_max"):
+        a, c = t(res[0][1][name]), t(res[1][1][name])
+        total = torch.maximum(a, c) if name == "dens_max" else a + c
+        for r in range(world):
+            assert torch.equal(t(res[r][2][name]), total), name
+    # independent dsh: autograd of colour = sum_k basis_k(dir) * sh_k (the forward polynomial of forward.cu:20-72) w.r.t. sh
+    import gof_dp
+    means = t(res[0][3])
+    want = torch.zeros(means.shape[0], 16, 3, dtype=torch.float64)
+    for r in range(world):
+        cam, degree, rgb = t(res[r][4]).double(), res[r][5], t(res[r][1]["dsh_rgb"]).double()
+        sh = torch.zeros(means.shape[0], 16, 3, dtype=torch.float64, requires_grad=True)
+        d = means.double() - cam
+        d = d / d.norm(dim=1, keepdim=True)
+        basis = gof_dp.sh_grad_weights_torch(d, degree)                      # the basis IS d colour / d sh
+        colour = (basis[:, :, None] * sh[:, :basis.shape[1], :]).sum(1)
+        (g,) = torch.autograd.grad(colour, sh, grad_outputs=rgb)
+        want += g
+    for r in range(world):
+        got = t(res[r][2]["dsh"]).double()
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    assert torch.equal(t(res[0][2]["dsh"]), t(res[1][2]["dsh"]))              # same bits on both ranks
+    # degree 2 on rank 1: its coefficients 9..15 carry rank 0's contribution only
+    assert float(t(res[0][2]["dsh"])[:, 9:, :].abs().sum()) > 0
+
+
+def test_sh_basis_matches_reference_forward_polynomial():
+    """gof_dp.sh_grad_weights_torch is the SH basis of the reference's forward (forward.cu:20-72): evaluated against the
+    closed-form real spherical harmonics constants at a few directions."""
+    import gof_dp
+    d = torch.tensor([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.6, 0.0, 0.8]], dtype=torch.float64)
+    w = gof_dp.sh_grad_weights_torch(d, 3)
+    assert w.shape == (3, 16)
+    assert torch.allclose(w[:, 0], torch.full((3,), 0.28209479177387814, dtype=torch.float64))
+    assert torch.allclose(w[0, 1:4], torch.tensor([0.0, 0.4886025119029199, 0.0], dtype=torch.float64))       # -C1 y, C1 z, -C1 x at +z
+    assert torch.allclose(w[1, 1:4], torch.tensor([0.0, 0.0, -0.4886025119029199], dtype=torch.float64))
+    assert abs(float(w[0, 6]) - 0.31539156525252005 * 2.0) < 1e-12                                                # C2_2 (2zz - xx - yy) at +z
+    assert abs(float(w[2, 7]) - (-1.0925484305920792 * 0.48)) < 1e-12                                             # C2_3 xz

@@ -117,3 +117,80 @@ def test_conv3x3_weight_gradient_kernel():
         assert _util.rel_err(conv.weight.grad, conv64.weight.grad)[0] < 2e-5, (co, ci)
         assert _util.rel_err(conv.bias.grad, conv64.bias.grad)[0] < 2e-5
         assert _util.rel_err(x.grad, x64.grad)[0] < 5e-3          # cuDNN's TF32 data gradient
+
+
+@pytest.mark.parametrize("P,degrees", [(30_011, (3, 3, 3)), (4_097, (3, 1, 2))])
+def test_factored_sh_gradient_is_the_sum_of_the_views(P, degrees):
+    """View-parallel exchange (csrc/sh_views.cu): the backward asked for the factored SH gradient leaves dL_dRGB + the camera
+    centre (and every other output unchanged); gof_sh_grad_from_views over three views' records is BIT-identical to adding the
+    three dL_dsh tensors of the plain backward in view order (backward.cu:45-139 is an outer product per view)."""
+    import ctypes
+    from diff_gaussian_rasterization import _C
+    import gof_dp
+    dev = torch.device("cuda")
+    H, W = 208, 320
+    slot = gof_dp.SH_SLOT_HEADER + (3 * P + 63) // 64 * 64
+    records = torch.full((3 * slot,), float("nan"), device=dev)
+    grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(2)).to(dev)
+    want, means = None, None
+    for i, (view, deg) in enumerate(zip((4, 11, 23), degrees)):
+        cam, gs = gof_synth.make_scene(dict(P=P, width=W, height=H, seed=17), view=view)
+        fa = _util.fwd_args(cam, gs, dev, sh_degree=deg)
+        R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
+        plain = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad))
+        rec = records[i * slot:(i + 1) * slot]
+        out = {"sh_hdr": rec[:gof_dp.SH_SLOT_HEADER], "dsh_rgb": rec[gof_dp.SH_SLOT_HEADER:gof_dp.SH_SLOT_HEADER + 3 * P].view(P, 3)}
+        fact = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=out)
+        torch.cuda.synchronize()
+        assert fact[5] is None and out["_means3D"].data_ptr() == fa[1].data_ptr()
+        for k in (0, 1, 2, 3, 4, 6, 7, 8):
+            assert torch.equal(plain[k], fact[k]), k
+        assert torch.equal(rec[:3], fa[19]) and float(rec[3]) == deg
+        assert not torch.isnan(out["dsh_rgb"]).any()
+        assert torch.equal(out["dsh_rgb"][radii == 0], torch.zeros_like(out["dsh_rgb"][radii == 0]))
+        want = plain[5].clone() if want is None else want + plain[5]
+        means = fa[1]
+    got = torch.full((P, 16, 3), float("nan"), device=dev)
+    ptrs = (ctypes.c_void_p * 3)(*[records.data_ptr() + 4 * i * slot for i in range(3)])
+    _C._check(_C._lib.gof_sh_grad_from_views(P, 16, 3, means.data_ptr(), ptrs, got.data_ptr(), _C._stream()))
+    torch.cuda.synchronize()
+    assert float(want.abs().max()) > 0
+    assert torch.equal(got, want)
+    # ... and the torch statement of the same sum (the CPU buckets of the gloo tests) agrees to rounding
+    ref = gof_dp.sh_grad_from_views_torch(means, [records[i * slot:(i + 1) * slot] for i in range(3)], P, 16)
+    assert _util.rel_err(ref, want)[0] < 1e-5
+
+
+def test_public_rasterizer_writes_into_grad_bucket():
+    """`GaussianRasterizer(settings, grad_bucket=bucket)` (extension): loss.backward() through the public autograd wrapper leaves
+    the parameter gradients and the densification statistics in the bucket -- bit-identical to the .grad tensors of the plain
+    wrapper -- and hands nothing but dL_dmeans2D back to autograd."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    dev = torch.device("cuda")
+    P, H, W = 20_003, 208, 320
+    cam, gs = gof_synth.make_scene(dict(P=P, width=W, height=H, seed=17), view=4)
+    rs = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, kernel_size=0.0,
+        subpixel_offset=torch.zeros(H, W, 2, device=dev), bg=torch.zeros(3, device=dev), scale_modifier=1.0,
+        viewmatrix=cam.world_view_transform.to(dev), projmatrix=cam.full_proj_transform.to(dev), sh_degree=3,
+        campos=cam.camera_center.to(dev), prefiltered=False, debug=False)
+    wgt = torch.randn(9, H, W, generator=torch.Generator().manual_seed(3)).to(dev)
+
+    def run(bucket):
+        params = {k: gs[k].to(dev).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
+        r = GaussianRasterizer(rs) if bucket is None else GaussianRasterizer(rs, grad_bucket=bucket)
+        img, radii = r(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"], shs=params["shs"],
+                       scales=params["scales"], rotations=params["rotations"])
+        (img * wgt).sum().backward()
+        return params, means2D, radii
+
+    params, m2d, radii = run(None)
+    bucket = gof_dp.GradBucket(P, 16, dev)
+    params_b, m2d_b, _ = run(bucket)
+    torch.cuda.synchronize()
+    for name, key in (("means3D", "dmeans3D"), ("shs", "dsh"), ("opacities", "dopacity"), ("scales", "dscales"), ("rotations", "drot")):
+        assert params_b[name].grad is None
+        assert torch.equal(bucket.views[key], params[name].grad), name
+    assert torch.equal(m2d_b.grad, m2d.grad)
+    assert torch.equal(bucket.views["dens_max"][:, 1], radii.float())

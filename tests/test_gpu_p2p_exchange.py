@@ -65,3 +65,71 @@ def test_exchange_kernels_equal_nccl(mode):
     (_, a0, r0), (_, a1, r1) = res
     np.testing.assert_array_equal(a0.view(np.int32), a1.view(np.int32))     # same bits on both ranks
     np.testing.assert_array_equal(a0.view(np.int32), r0.view(np.int32))     # and NCCL's bits (two addends / exact max)
+
+
+def _worker_factored(rank, world, port, q, mode):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import _util
+    import gof_dp
+    import gof_synth
+    from diff_gaussian_rasterization import _C
+    P, H, W = 50_003, 208, 320
+    cam, gs = gof_synth.make_scene(dict(P=P, width=W, height=H, seed=17), view=3 + 7 * rank)     # a different view per rank
+    fa = _util.fwd_args(cam, gs, dev)
+    R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
+    grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(2)).to(dev)
+    plain_b = gof_dp.GradBucket(P, 16, dev)                      # the unfactored bucket, NCCL: the result to reproduce
+    _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=plain_b.views)
+    plain_b.all_reduce()
+    bucket = gof_dp.GradBucket(P, 16, dev, factor_sh=True)
+    try:
+        if mode == "nvls":
+            bucket.enable_nvls_exchange()
+        elif mode == "p2p":
+            bucket.enable_peer_exchange()
+    except Exception as e:   # noqa: BLE001 -- symmetric on all ranks
+        q.put((rank, "unavailable: " + str(e)[:200], None))
+        dist.barrier(); dist.destroy_process_group()
+        return
+    assert bucket.exchange == mode and bucket.factored and bucket.flat.numel() * 4 < 0.45 * plain_b.flat.numel() * 4
+    for it in range(2):                                          # repeated use: the records are rewritten every step
+        _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=bucket.views)
+        bucket.all_reduce()
+    torch.cuda.synchronize()
+    out = {}
+    for name in ("dmeans3D", "dsh", "dopacity", "dscales", "drot", "dens_sum", "dens_max"):
+        out[name] = (bucket.views[name].cpu().numpy().copy(), plain_b.views[name].cpu().numpy().copy())
+    q.put((rank, out, None))
+    bucket.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "nvls"])
+def test_factored_exchange_equals_plain_allreduce(mode):
+    """GradBucket(factor_sh=True) on two GPUs rendering different views: after all_reduce() every field -- dL_dsh expanded from
+    the two views' dL_dRGB records included -- carries the same bits as NCCL's all-reduce of the unfactored 64-float bucket
+    (two addends: the sum does not depend on the order), on both ranks, for every exchange mode."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one node")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_factored, args=(r, 2, port, q, mode)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    if isinstance(res[0][1], str):
+        pytest.skip(f"{mode} exchange {res[0][1]}")
+    for name in res[0][1]:
+        a0, r0 = res[0][1][name]
+        a1, _ = res[1][1][name]
+        assert np.abs(r0).max() > 0, name
+        np.testing.assert_array_equal(a0.view(np.int32), a1.view(np.int32), err_msg=name)     # same bits on both ranks
+        np.testing.assert_array_equal(a0, r0, err_msg=name)                                   # and the plain all-reduce's values
