@@ -212,7 +212,8 @@ class GradBucket:
         self.all_reduce(group=group, _expand=False)
         torch.cuda.synchronize(dev)
         good = bool((self.flat[:self.n_sum] == float(world)).all().item()) and bool((self.flat[self.n_sum:self.n_reduce] == 1.0).all().item())
-        good = agree(good and self._selftest_records(group))
+        rec_ok = self._selftest_records(group)       # collective: evaluated on every rank, whatever `good` says
+        good = agree(good and rec_ok)
         self.flat.zero_()
         if not good:
             self.close()
@@ -315,7 +316,8 @@ class GradBucket:
         torch.cuda.synchronize(dev)
         good = bool((self.flat[:self.n_sum] == float(world * (world + 1) // 2)).all().item()) and \
             bool((self.flat[self.n_sum:self.n_reduce] == float(world - 1)).all().item())
-        good = agree(good and self._selftest_records(group))
+        rec_ok = self._selftest_records(group)       # collective: evaluated on every rank, whatever `good` says
+        good = agree(good and rec_ok)
         self.flat.zero_()
         if not good:
             self.flat, self.views, self.exchange = old
