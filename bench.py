@@ -164,15 +164,20 @@ def bwd_args(fa, radii, geom, R, binning, img, grad):
             campos, geom, R, binning, img, dbg)
 
 
+NCU_SUMMARY = "profiles/r2_ncu_render_call7.txt"      # ncu --set full of the shipped kernels at C3 (sections "Kernel Name ...")
+
+
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` at this workload, from the committed
-    `ncu --set full` summary (profiles/r1_final_<kernel>.txt); None if the file is missing."""
-    path = os.path.join(ROOT, "profiles", f"r1_final_{kernel}.txt")
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` ("render_fwd" / "render_bwd") at the C3 workload,
+    from the committed `ncu --set full` summary; None if the file or the kernel's section is missing."""
+    want = {"render_bwd": "k_render_backward", "render_fwd": "k_render_forward"}.get(kernel, kernel)
     try:
-        tot = 0.0
-        for ln in open(path):
+        tot, inside = 0.0, False
+        for ln in open(os.path.join(ROOT, NCU_SUMMARY)):
             f = ln.split()
-            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if ln.startswith("Kernel Name"):
+                inside = want in ln
+            elif inside and len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
         return tot or None
     except Exception:
@@ -380,18 +385,23 @@ def run_ours(args, rank, world, dev):
         step_device(s)
     exchange_check = None
     if world > 1:   # untimed: the exchanged bucket equals the combination of the per-rank single-GPU results
-        # every rank's OWN gradients from a plain single-GPU backward into an unfactored local bucket (full dL_dsh) ...
+        # ONE backward per rank into the exchanged bucket (two runs would differ in the last bits: float atomics in the blend
+        # kernel); a factored bucket additionally receives this view's own full dL_dsh (checks only) ...
         fa = wl.fwd_args(wl.view(0))
         R0, _c0, radii0, geom0, bin0, img0 = _C.rasterize_gaussians(*fa)
-        single = gof_dp.GradBucket(wl.P, 16, dev)
-        _C.rasterize_gaussians_backward(*bwd_args(fa, radii0, geom0, R0, bin0, img0, wl.dL), _out=single.views)
-        # ... against the same backward into the exchanged bucket
         bucket.zero_()
-        _C.rasterize_gaussians_backward(*bwd_args(fa, radii0, geom0, R0, bin0, img0, wl.dL), _out=bucket.views)
-        bucket.all_reduce()
+        views = dict(bucket.views)
+        full = None
+        if bucket.factored:
+            full = torch.empty(wl.P, 16, 3, device=dev)
+            views["_dsh_full"] = full
+        _C.rasterize_gaussians_backward(*bwd_args(fa, radii0, geom0, R0, bin0, img0, wl.dL), _out=views)
+        names = ("dmeans3D", "dsh", "dopacity", "dscales", "drot", "dens_sum", "dens_max")
+        single = {n: (full if (n == "dsh" and bucket.factored) else bucket.views[n].clone()) for n in names}    # ... kept per rank ...
+        bucket.all_reduce(means3D=fa[1])                                                                        # ... and exchanged
         err, ok_max = 0.0, True
-        for name in ("dmeans3D", "dsh", "dopacity", "dscales", "drot", "dens_sum", "dens_max"):
-            mine = single.views[name].contiguous()
+        for name in names:
+            mine = single[name].contiguous()
             parts = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(parts, mine)
             got = bucket.views[name]
@@ -410,7 +420,7 @@ def run_ours(args, rank, world, dev):
         flag = torch.tensor([1.0 if (ok_sum and ok_max and float(lo) == float(hi)) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         exchange_check = "ok" if float(flag.item()) == 1.0 else f"FAILED (sum err {err:.3g}, max ok {ok_max}, identical on ranks {float(lo) == float(hi)})"
-        del single, geom0, bin0, img0
+        del single, full, views, geom0, bin0, img0
     barrier_sync(world)
     launches0 = _C.launch_count()
     sampler = ClockSampler(torch.cuda.current_device())
@@ -496,7 +506,7 @@ def run_ours(args, rank, world, dev):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(dom),
-                     "traffic_source": f"profiles/r1_final_{dom}.txt (ncu --set full, same workload, per launch)",
+                     "traffic_source": f"{NCU_SUMMARY} (ncu --set full, C3 workload, per launch)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms / max(dom_cnt, 1),
                      "step_algorithmic_bytes": step_bytes,

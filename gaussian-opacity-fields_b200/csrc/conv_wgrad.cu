@@ -4,17 +4,12 @@
 // cuDNN answers these shapes with its generic fp32 `wgrad_alg0_engine` -- 2.1 ms of the 5.2 ms appearance step, more than the
 // whole forward of the network.  dW[co][ci][ky][kx] = sum_p gy[co][p] * x[ci][p + (ky-1, kx-1)] is a reduction over two million
 // pixels into at most 2304 numbers: here one thread owns a few (co, ci) pairs and keeps their nine sums each in registers while
-// persistent CTAs sweep pixel tiles staged in shared memory by cp.async (a 3x3 window of x slides along the row); one atomic flush
-// per CTA.  fp32 accumulation (cuDNN's TF32 path rounds the products to 10 bits).
+// persistent CTAs sweep pixel tiles staged in shared memory (a 3x3 window of x slides along the row); one atomic flush per CTA.  fp32 accumulation (cuDNN's TF32 path rounds the products to 10 bits).
 #include "gof_common.cuh"
 
 namespace {
 
 constexpr int TW = 32, TH = 8;   // pixel tile
-
-__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const float* src, bool valid) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
-}
 
 // COPT output channels per thread (register tile: 3 + COPT shared loads per 9*COPT FMAs), RG row groups per tile (so that small
 // channel pairs still fill a CTA): THREADS = CO/COPT * CI * RG.
@@ -24,12 +19,15 @@ __global__ void __launch_bounds__((CO / COPT) * CI * RG) k_conv3x3_wgrad(const f
   constexpr int THREADS = (CO / COPT) * CI * RG;
   constexpr int ROWS = TH / RG;
   static_assert(CO % COPT == 0 && TH % RG == 0 && THREADS >= 64 && THREADS <= 1024, "tile shape");
-  constexpr int XP = (TH + 2) * (TW + 2) + 1;   // plane pitch of the x tile (+1: the CI planes fall into distinct banks)
-  constexpr int GP = TH * TW + 1;
+  // Shared-memory pitches chosen for the lanes of a warp (CI channels x two row groups or output-channel groups): x planes
+  // 350 floats apart (== -2 mod 32: the CI planes take distinct even banks) with rows 35 apart (odd: the second row group takes the
+  // odd banks); g rows 33 apart, planes 265 apart (4 * 265 == 4 mod 32: the output-channel groups take distinct banks).
+  constexpr int XROW = TW + 3, XP = (TH + 2) * XROW;
+  constexpr int GROW = TW + 1, GP = TH * GROW + 1;
+  static_assert(TW == 32 && TH == 8, "pitches are worked out for 32x8 tiles");
   __shared__ float s_x[CI * XP];
   __shared__ float s_g[CO * GP];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t sx_base = (uint32_t)__cvta_generic_to_shared(s_x), sg_base = (uint32_t)__cvta_generic_to_shared(s_g);
+  const int tid = threadIdx.x;
   const int ci = tid % CI, cog = (tid / CI) % (CO / COPT), rg = tid / (CI * (CO / COPT));
   float acc[COPT][9], accb[COPT];
 #pragma unroll
@@ -43,44 +41,60 @@ __global__ void __launch_bounds__((CO / COPT) * CI * RG) k_conv3x3_wgrad(const f
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int y0 = ty * TH, x0 = tx * TW;
     __syncthreads();
-    // Fill with 4-byte cp.async (zero-filled outside the image): every copy of the tile is in flight before the first one is
-    // waited for -- a load/store loop serialised ~40 DRAM round trips per thread and tile (first version: 0.59 ms for the
-    // 16 -> 3 layer).  One warp per tile row: the row/plane index arithmetic is per row, not per element.
-    for (int r = warp; r < CI * (TH + 2); r += THREADS / 32) {
-      const int c = r / (TH + 2), yy = r - c * (TH + 2);
-      const int iy = y0 + yy - 1;
-      const bool rowok = iy >= 0 && iy < H;
-      const float* src = x + (size_t)c * HW + (size_t)(rowok ? iy : 0) * W;
-      const uint32_t dst = sx_base + 4u * (uint32_t)(c * XP + yy * (TW + 2));
+    // Fill: batches of eight independent loads per thread, then eight stores.  (A plain load/store loop serialised ~40 DRAM
+    // round trips per thread and tile -- 0.59 ms for the 16 -> 3 layer; 4-byte cp.async copies measured slower still.)
+    constexpr int NX = CI * (TH + 2) * (TW + 2), NG = CO * TH * TW;
+#pragma unroll 1
+    for (int base = 0; base < NX; base += THREADS * 8) {
+      float v[8];
 #pragma unroll
-      for (int xx = lane; xx < TW + 2; xx += 32) {
-        const int ix = x0 + xx - 1;
-        const bool ok = rowok && ix >= 0 && ix < W;
-        cp_async4_zfill(dst + 4u * (uint32_t)xx, src + (ok ? ix : 0), ok);
+      for (int u = 0; u < 8; ++u) {
+        const int e = base + u * THREADS + tid;
+        const int c = e / ((TH + 2) * (TW + 2)), r = e - c * ((TH + 2) * (TW + 2));
+        const int yy = r / (TW + 2), xx = r - yy * (TW + 2);
+        const int iy = y0 + yy - 1, ix = x0 + xx - 1;
+        v[u] = (e < NX && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (size_t)c * HW + (size_t)iy * W + ix) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = base + u * THREADS + tid;
+        const int c = e / ((TH + 2) * (TW + 2)), r = e - c * ((TH + 2) * (TW + 2));
+        const int yy = r / (TW + 2), xx = r - yy * (TW + 2);
+        if (e < NX) s_x[c * XP + yy * XROW + xx] = v[u];
       }
     }
-    for (int r = warp; r < CO * TH; r += THREADS / 32) {
-      const int c = r / TH, yy = r - c * TH;
-      const int iy = y0 + yy, ix = x0 + lane;
-      const bool ok = iy < H && ix < W;
-      cp_async4_zfill(sg_base + 4u * (uint32_t)(c * GP + yy * TW + lane), gy + (size_t)c * HW + (ok ? (size_t)iy * W + ix : 0), ok);
+#pragma unroll 1
+    for (int base = 0; base < NG; base += THREADS * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = base + u * THREADS + tid;
+        const int c = e / (TH * TW), r = e - c * (TH * TW);
+        const int iy = y0 + r / TW, ix = x0 + (r & (TW - 1));
+        v[u] = (e < NG && iy < H && ix < W) ? __ldg(gy + (size_t)c * HW + (size_t)iy * W + ix) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = base + u * THREADS + tid;
+        const int c = e / (TH * TW), r = e - c * (TH * TW);
+        if (e < NG) s_g[c * GP + (r / TW) * GROW + (r & (TW - 1))] = v[u];
+      }
     }
-    gof_cp_async_wait_all();
     __syncthreads();
     const float* xs = s_x + ci * XP;
     const float* gs = s_g + cog * COPT * GP;
 #pragma unroll 1
     for (int yy = rg * ROWS; yy < rg * ROWS + ROWS; ++yy) {
-      const float* r0 = xs + yy * (TW + 2);
-      const float* r1 = r0 + (TW + 2);
-      const float* r2 = r1 + (TW + 2);
+      const float* r0 = xs + yy * XROW;
+      const float* r1 = r0 + XROW;
+      const float* r2 = r1 + XROW;
       float a0 = r0[0], a1 = r0[1], b0 = r1[0], b1 = r1[1], c0 = r2[0], c1 = r2[1];
 #pragma unroll 8
       for (int xx = 0; xx < TW; ++xx) {
         const float a2 = r0[xx + 2], b2 = r1[xx + 2], c2 = r2[xx + 2];
 #pragma unroll
         for (int j = 0; j < COPT; ++j) {
-          const float g = gs[j * GP + yy * TW + xx];
+          const float g = gs[j * GP + yy * GROW + xx];
           acc[j][0] = fmaf(g, a0, acc[j][0]); acc[j][1] = fmaf(g, a1, acc[j][1]); acc[j][2] = fmaf(g, a2, acc[j][2]);
           acc[j][3] = fmaf(g, b0, acc[j][3]); acc[j][4] = fmaf(g, b1, acc[j][4]); acc[j][5] = fmaf(g, b2, acc[j][5]);
           acc[j][6] = fmaf(g, c0, acc[j][6]); acc[j][7] = fmaf(g, c1, acc[j][7]); acc[j][8] = fmaf(g, c2, acc[j][8]);

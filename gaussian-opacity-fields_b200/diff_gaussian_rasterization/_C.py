@@ -268,6 +268,10 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  and rgb_t.dtype == torch.float32 and hdr_t.dtype == torch.float32):
             raise RuntimeError("gof_b200: _out['dsh_rgb'] must be a contiguous float32 (P,3) tensor and _out['sh_hdr'] hold >= 4 floats")
         _out["_means3D"] = means3D if means3D.is_contiguous() else means3D.contiguous()
+        full_t = _out.get("_dsh_full")      # checks only: ALSO write this view's own dL_dsh (P,M,3), from the same dL_dRGB
+        if full_t is not None and not (full_t.is_contiguous() and tuple(full_t.shape) == (P, M, 3) and full_t.dtype == torch.float32
+                                       and not (full_t.data_ptr() & 15)):
+            raise RuntimeError("gof_b200: _out['_dsh_full'] must be a contiguous, 16-byte aligned float32 (P,M,3) tensor")
     need = {k: v for k, v in shapes.items() if not (_out is not None and k in _out) and not (factored and k == "dsh")}
     offs, total = {}, 0
     for k, shp in need.items():
@@ -319,7 +323,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 ctypes.byref(s), int(R), _ptr(rad, torch.int32), _ptr(geomBuffer, torch.uint8),
                 _ptr(binningBuffer, torch.uint8), _ptr(imageBuffer, torch.uint8), _ptr(g),
                 dL_dmeans2D.data_ptr(), None, dL_dopacity.data_ptr(), dL_dcolors.data_ptr(),
-                dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), None if factored else _ptr(dL_dsh), dL_dscales.data_ptr(),
+                dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), (_ptr(full_t) if full_t is not None else None) if factored else _ptr(dL_dsh),
+                dL_dscales.data_ptr(),
                 dL_drotations.data_ptr(), dL_dv2g.data_ptr(), ds.data_ptr() if ds is not None else None,
                 dm.data_ptr() if dm is not None else None, rgb_t.data_ptr() if factored else None,
                 hdr_t.data_ptr() if factored else None, _stream()))

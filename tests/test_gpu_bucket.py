@@ -139,16 +139,21 @@ def test_factored_sh_gradient_is_the_sum_of_the_views(P, degrees):
         R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
         plain = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad))
         rec = records[i * slot:(i + 1) * slot]
-        out = {"sh_hdr": rec[:gof_dp.SH_SLOT_HEADER], "dsh_rgb": rec[gof_dp.SH_SLOT_HEADER:gof_dp.SH_SLOT_HEADER + 3 * P].view(P, 3)}
+        # ONE backward leaves both the record and (checks only: "_dsh_full") this view's own dL_dsh -- the blend kernel's float
+        # atomics make two backward runs differ in the last bits, so the bit-exact statement needs both from the same run
+        full = torch.full((P, 16, 3), float("nan"), device=dev)
+        out = {"sh_hdr": rec[:gof_dp.SH_SLOT_HEADER], "dsh_rgb": rec[gof_dp.SH_SLOT_HEADER:gof_dp.SH_SLOT_HEADER + 3 * P].view(P, 3),
+               "_dsh_full": full}
         fact = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=out)
         torch.cuda.synchronize()
         assert fact[5] is None and out["_means3D"].data_ptr() == fa[1].data_ptr()
-        for k in (0, 1, 2, 3, 4, 6, 7, 8):
-            assert torch.equal(plain[k], fact[k]), k
+        for k in (0, 1, 2, 3, 4, 6, 7, 8):           # the other outputs: the plain backward's, up to the atomics' run-to-run noise
+            assert _util.rel_err(fact[k], plain[k])[1] < 1e-4 or float(plain[k].abs().max()) == 0.0, k
+        assert _util.rel_err(full, plain[5])[1] < 1e-4
         assert torch.equal(rec[:3], fa[19]) and float(rec[3]) == deg
-        assert not torch.isnan(out["dsh_rgb"]).any()
+        assert not torch.isnan(out["dsh_rgb"]).any() and not torch.isnan(full).any()
         assert torch.equal(out["dsh_rgb"][radii == 0], torch.zeros_like(out["dsh_rgb"][radii == 0]))
-        want = plain[5].clone() if want is None else want + plain[5]
+        want = full.clone() if want is None else want + full
         means = fa[1]
     got = torch.full((P, 16, 3), float("nan"), device=dev)
     ptrs = (ctypes.c_void_p * 3)(*[records.data_ptr() + 4 * i * slot for i in range(3)])
@@ -163,8 +168,8 @@ def test_factored_sh_gradient_is_the_sum_of_the_views(P, degrees):
 
 def test_public_rasterizer_writes_into_grad_bucket():
     """`GaussianRasterizer(settings, grad_bucket=bucket)` (extension): loss.backward() through the public autograd wrapper leaves
-    the parameter gradients and the densification statistics in the bucket -- bit-identical to the .grad tensors of the plain
-    wrapper -- and hands nothing but dL_dmeans2D back to autograd."""
+    the parameter gradients and the densification statistics in the bucket -- the .grad tensors of the plain wrapper -- and hands
+    nothing but dL_dmeans2D back to autograd."""
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     dev = torch.device("cuda")
     P, H, W = 20_003, 208, 320
@@ -191,6 +196,7 @@ def test_public_rasterizer_writes_into_grad_bucket():
     torch.cuda.synchronize()
     for name, key in (("means3D", "dmeans3D"), ("shs", "dsh"), ("opacities", "dopacity"), ("scales", "dscales"), ("rotations", "drot")):
         assert params_b[name].grad is None
-        assert torch.equal(bucket.views[key], params[name].grad), name
-    assert torch.equal(m2d_b.grad, m2d.grad)
+        # (two backward runs: equal up to the blend kernel's float-atomic ordering)
+        assert _util.rel_err(bucket.views[key].reshape(params[name].grad.shape), params[name].grad)[1] < 1e-4, name
+    assert _util.rel_err(m2d_b.grad, m2d.grad)[1] < 1e-4
     assert torch.equal(bucket.views["dens_max"][:, 1], radii.float())

@@ -108,13 +108,15 @@ try:
                 for unroll in (1, 2, 4, 8):
                     if mode != 3 and (unroll not in (2, 8) or layout == 0 and threads != 512):
                         continue
+                    if threads * unroll > 2048:      # the unrolled variants do not fit 1024-thread CTAs (registers)
+                        continue
                     ms = timed(lambda: nvls(sms * per_sm, threads, unroll, layout, mode))
                     report(kind="nvls_probe", mode=mode, layout=layout, threads=threads, ctas_per_sm=per_sm, unroll=unroll, ms=ms)
     # grids that are NOT a multiple of the SM count (few fat CTAs, NCCL-like)
     for grid in (16, 32, 64, 128):
         for unroll in (4, 8):
-            ms = timed(lambda: nvls(grid, 1024, unroll, 1, 3))
-            report(kind="nvls_probe", mode=3, layout=1, threads=1024, grid=grid, unroll=unroll, ms=ms)
+            ms = timed(lambda: nvls(grid, 512, unroll, 1, 3))
+            report(kind="nvls_probe", mode=3, layout=1, threads=512, grid=grid, unroll=unroll, ms=ms)
     bucket.close()
 except Exception as e:  # noqa: BLE001
     report(kind="nvls", error=f"{type(e).__name__}: {str(e)[:300]}")
@@ -140,7 +142,7 @@ try:
         for layout in (0, 1):
             for threads, per_sm in ((512, 4), (512, 2), (512, 1), (1024, 2), (1024, 1), (256, 8), (256, 4)):
                 for unroll in (1, 2, 4, 8):
-                    if unroll > max_unroll:
+                    if unroll > max_unroll or threads * unroll * world > 4096:
                         continue
                     ms = timed(lambda: p2p(sms * per_sm, threads, unroll, layout))
                     report(kind="p2p_probe", layout=layout, threads=threads, ctas_per_sm=per_sm, unroll=unroll, ms=ms)
