@@ -399,7 +399,7 @@ def run_ours(args, rank, world, dev):
         names = ("dmeans3D", "dsh", "dopacity", "dscales", "drot", "dens_sum", "dens_max")
         single = {n: (full if (n == "dsh" and bucket.factored) else bucket.views[n].clone()) for n in names}    # ... kept per rank ...
         bucket.all_reduce(means3D=fa[1])                                                                        # ... and exchanged
-        err, ok_max = 0.0, True
+        err, ok_max, errs = 0.0, True, {}
         for name in names:
             mine = single[name].contiguous()
             parts = [torch.empty_like(mine) for _ in range(world)]
@@ -410,7 +410,8 @@ def run_ours(args, rank, world, dev):
             else:
                 st = torch.stack(parts).double()
                 want, mag = st.sum(0), st.abs().sum(0)
-                err = max(err, float(((got.double() - want).abs() / (1e-6 * mag + 1e-30)).max()))      # <= 1: within 1e-6 of the magnitude sum
+                errs[name] = float(((got.double() - want).abs() / (1e-6 * mag + 1e-30)).max())      # <= 1: within 1e-6 of the magnitude sum
+                err = max(err, errs[name])
             del parts
         ok_sum = err <= 1.0
         same = torch.tensor([float(bucket.flat[:bucket.n_reduce].double().sum()) + float(bucket.views["dsh"].double().sum())],
@@ -419,7 +420,7 @@ def run_ours(args, rank, world, dev):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         flag = torch.tensor([1.0 if (ok_sum and ok_max and float(lo) == float(hi)) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        exchange_check = "ok" if float(flag.item()) == 1.0 else f"FAILED (sum err {err:.3g}, max ok {ok_max}, identical on ranks {float(lo) == float(hi)})"
+        exchange_check = "ok" if float(flag.item()) == 1.0 else f"FAILED (sum err {err:.3g} {errs}, max ok {ok_max}, identical on ranks {float(lo) == float(hi)})"
         del single, full, views, geom0, bin0, img0
     barrier_sync(world)
     launches0 = _C.launch_count()
