@@ -13,7 +13,7 @@ constexpr int TW = 32, TH = 8;   // pixel tile
 
 // COPT output channels per thread (register tile: 3 + COPT shared loads per 9*COPT FMAs), RG row groups per tile (so that small
 // channel pairs still fill a CTA): THREADS = CO/COPT * CI * RG.
-template <int CO, int CI, int COPT, int RG>
+template <int CO, int CI, int COPT, int RG, bool VEC>
 __global__ void __launch_bounds__((CO / COPT) * CI * RG) k_conv3x3_wgrad(const float* __restrict__ x, const float* __restrict__ gy, int H, int W,
                                                                           int tiles_x, int tiles, float* __restrict__ dW, float* __restrict__ db) {
   constexpr int THREADS = (CO / COPT) * CI * RG;
@@ -41,43 +41,54 @@ __global__ void __launch_bounds__((CO / COPT) * CI * RG) k_conv3x3_wgrad(const f
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int y0 = ty * TH, x0 = tx * TW;
     __syncthreads();
-    // Fill: batches of eight independent loads per thread, then eight stores.  (A plain load/store loop serialised ~40 DRAM
-    // round trips per thread and tile -- 0.59 ms for the 16 -> 3 layer; 4-byte cp.async copies measured slower still.)
-    constexpr int NX = CI * (TH + 2) * (TW + 2), NG = CO * TH * TW;
-#pragma unroll 1
-    for (int base = 0; base < NX; base += THREADS * 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = base + u * THREADS + tid;
+    if (VEC) {
+      // Fill, W % 4 == 0 and 16-byte aligned planes: the 32 interior floats of a tile row are eight aligned LDG.128, the two halo
+      // columns scalar loads -- 12 DRAM round trips per thread and tile instead of 42 (ptxas pairs every load with its stores
+      // through one register whatever the source order, so the number of loads is what counts; ncu of the scalar version: 23
+      // warps per issue waiting on the scoreboard, 0.93 ms for the 16 -> 3 layer).
+      constexpr int XG = CI * (TH + 2) * (TW / 4), XH = CI * (TH + 2) * 2, GG = CO * TH * (TW / 4);
+#pragma unroll 2
+      for (int g = tid; g < XG; g += THREADS) {
+        const int c = g / ((TH + 2) * (TW / 4)), r = g - c * ((TH + 2) * (TW / 4));
+        const int yy = r / (TW / 4), k = r - yy * (TW / 4);
+        const int iy = y0 + yy - 1, ix = x0 + 4 * k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < H && ix < W) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)c * HW + (size_t)iy * W + ix));
+        float* d = s_x + c * XP + yy * XROW + 1 + 4 * k;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+#pragma unroll 2
+      for (int h = tid; h < XH; h += THREADS) {
+        const int c = h / ((TH + 2) * 2), r = h - c * ((TH + 2) * 2);
+        const int yy = r >> 1, side = r & 1;
+        const int iy = y0 + yy - 1, ix = side ? x0 + TW : x0 - 1;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (size_t)c * HW + (size_t)iy * W + ix);
+        s_x[c * XP + yy * XROW + (side ? TW + 1 : 0)] = v;
+      }
+#pragma unroll 2
+      for (int g = tid; g < GG; g += THREADS) {
+        const int c = g / (TH * (TW / 4)), r = g - c * (TH * (TW / 4));
+        const int yy = r / (TW / 4), k = r - yy * (TW / 4);
+        const int iy = y0 + yy, ix = x0 + 4 * k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy < H && ix < W) v = __ldg(reinterpret_cast<const float4*>(gy + (size_t)c * HW + (size_t)iy * W + ix));
+        float* d = s_g + c * GP + yy * GROW + 4 * k;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      // any W / alignment: scalar loads
+      constexpr int NX = CI * (TH + 2) * (TW + 2), NG = CO * TH * TW;
+      for (int e = tid; e < NX; e += THREADS) {
         const int c = e / ((TH + 2) * (TW + 2)), r = e - c * ((TH + 2) * (TW + 2));
         const int yy = r / (TW + 2), xx = r - yy * (TW + 2);
         const int iy = y0 + yy - 1, ix = x0 + xx - 1;
-        v[u] = (e < NX && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (size_t)c * HW + (size_t)iy * W + ix) : 0.f;
+        s_x[c * XP + yy * XROW + xx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (size_t)c * HW + (size_t)iy * W + ix) : 0.f;
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = base + u * THREADS + tid;
-        const int c = e / ((TH + 2) * (TW + 2)), r = e - c * ((TH + 2) * (TW + 2));
-        const int yy = r / (TW + 2), xx = r - yy * (TW + 2);
-        if (e < NX) s_x[c * XP + yy * XROW + xx] = v[u];
-      }
-    }
-#pragma unroll 1
-    for (int base = 0; base < NG; base += THREADS * 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = base + u * THREADS + tid;
+      for (int e = tid; e < NG; e += THREADS) {
         const int c = e / (TH * TW), r = e - c * (TH * TW);
         const int iy = y0 + r / TW, ix = x0 + (r & (TW - 1));
-        v[u] = (e < NG && iy < H && ix < W) ? __ldg(gy + (size_t)c * HW + (size_t)iy * W + ix) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = base + u * THREADS + tid;
-        const int c = e / (TH * TW), r = e - c * (TH * TW);
-        if (e < NG) s_g[c * GP + (r / TW) * GROW + (r & (TW - 1))] = v[u];
+        s_g[c * GP + (r / TW) * GROW + (r & (TW - 1))] = (iy < H && ix < W) ? __ldg(gy + (size_t)c * HW + (size_t)iy * W + ix) : 0.f;
       }
     }
     __syncthreads();
@@ -113,20 +124,26 @@ __global__ void __launch_bounds__((CO / COPT) * CI * RG) k_conv3x3_wgrad(const f
   }
 }
 
-template <int CO, int CI, int COPT, int RG>
-int launch(const float* x, const float* gy, int H, int W, float* dW, float* db, cudaStream_t st) {
+template <int CO, int CI, int COPT, int RG, bool VEC>
+int launch_v(const float* x, const float* gy, int H, int W, float* dW, float* db, cudaStream_t st) {
   constexpr int THREADS = (CO / COPT) * CI * RG;
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH, tiles = tiles_x * tiles_y;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   static int per_sm = 0;   // resident CTAs per SM of this instantiation: the persistent grid is exactly one wave
   if (!per_sm) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv3x3_wgrad<CO, CI, COPT, RG>, THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv3x3_wgrad<CO, CI, COPT, RG, VEC>, THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   }
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
-  GOF_LAUNCH("conv3x3_wgrad", st, (k_conv3x3_wgrad<CO, CI, COPT, RG><<<grid, THREADS, 0, st>>>(x, gy, H, W, tiles_x, tiles, dW, db)));
+  GOF_LAUNCH("conv3x3_wgrad", st, (k_conv3x3_wgrad<CO, CI, COPT, RG, VEC><<<grid, THREADS, 0, st>>>(x, gy, H, W, tiles_x, tiles, dW, db)));
   GOF_LAUNCH_CHECK(false, st);
   return GOF_OK;
+}
+
+template <int CO, int CI, int COPT, int RG>
+int launch(const float* x, const float* gy, int H, int W, float* dW, float* db, cudaStream_t st) {
+  const bool vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy)) & 15u) == 0;
+  return vec ? launch_v<CO, CI, COPT, RG, true>(x, gy, H, W, dW, db, st) : launch_v<CO, CI, COPT, RG, false>(x, gy, H, W, dW, db, st);
 }
 
 }  // namespace

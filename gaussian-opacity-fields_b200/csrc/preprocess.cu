@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
   // ---- computeColorFromSH backward, backward.cu:20-139 ----
   if (a.shs != nullptr) {
     const float dox = mx - a.cam_pos[0], doy = my - a.cam_pos[1], doz = mz - a.cam_pos[2];
-    const float len = sqrtf(dox * dox + doy * doy + doz * doz);
-    const float x = dox / len, y = doy / len, z = doz / len;
+    float x, y, z;
+    gof_sh_view_dir(mx, my, mz, a.cam_pos[0], a.cam_pos[1], a.cam_pos[2], &x, &y, &z);
     float sh[48];
     if (a.M == 16) {   // 192-byte rows: 12 x LDG.128
       const float4* src = reinterpret_cast<const float4*>(a.shs + (size_t)idx * 48);
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
       const int nk = (a.D + 1) * (a.D + 1);
 #pragma unroll
       for (int k = 0; k < 16; ++k)
-        if (k < nk) { dsh[3 * k] = w[k] * dRGB[0]; dsh[3 * k + 1] = w[k] * dRGB[1]; dsh[3 * k + 2] = w[k] * dRGB[2]; }
+        if (k < nk) { dsh[3 * k] = __fmul_rn(w[k], dRGB[0]); dsh[3 * k + 1] = __fmul_rn(w[k], dRGB[1]); dsh[3 * k + 2] = __fmul_rn(w[k], dRGB[2]); }
     }
     if (a.D > 0) {
 #pragma unroll

@@ -42,10 +42,8 @@ __global__ void __launch_bounds__(SHV_THREADS) k_sh_grad_from_views(const ShvArg
       const int D = (int)s_cam[v][3];
       maxD = D > maxD ? D : maxD;
       if (r == 0.f && g == 0.f && b == 0.f) continue;   // not seen by view v (or clamped in all channels): contributes +0
-      // the direction exactly as k_preprocess_backward forms it
-      const float dox = mx - s_cam[v][0], doy = my - s_cam[v][1], doz = mz - s_cam[v][2];
-      const float len = sqrtf(dox * dox + doy * doy + doz * doz);
-      const float x = dox / len, y = doy / len, z = doz / len;
+      float x, y, z;   // the direction exactly as k_preprocess_backward forms it
+      gof_sh_view_dir(mx, my, mz, s_cam[v][0], s_cam[v][1], s_cam[v][2], &x, &y, &z);
       float w[16];
       gof_sh_grad_weights(D, x, y, z, w);
       const int nk = (D + 1) * (D + 1);

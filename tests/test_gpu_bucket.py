@@ -103,7 +103,9 @@ def test_conv3x3_weight_gradient_kernel():
     import gof_appearance
     dev = torch.device("cuda")
     gen = torch.Generator().manual_seed(3)
-    for (co, ci), (H, W) in (((16, 16), (203, 333)), ((3, 16), (130, 200)), ((16, 8), (264, 129))):
+    # (W % 4 == 0: the kernel's vector fill; otherwise its scalar fill)
+    for (co, ci), (H, W) in (((16, 16), (203, 333)), ((16, 16), (130, 200)), ((3, 16), (130, 200)), ((3, 16), (131, 257)),
+                             ((16, 8), (264, 129)), ((16, 8), (136, 264))):
         conv = torch.nn.Conv2d(ci, co, 3, padding=1).to(dev)
         x = torch.randn(1, ci, H, W, generator=gen).to(dev).requires_grad_(True)
         gy = torch.randn(1, co, H, W, generator=gen).to(dev)
