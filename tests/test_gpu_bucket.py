@@ -121,21 +121,22 @@ def test_conv3x3_weight_gradient_kernel():
         assert _util.rel_err(x.grad, x64.grad)[0] < 5e-3          # cuDNN's TF32 data gradient
 
 
-@pytest.mark.parametrize("P,degrees", [(30_011, (3, 3, 3)), (4_097, (3, 1, 2))])
+@pytest.mark.parametrize("P,degrees", [(30_011, (3, 3, 3)), (4_097, (3, 1, 2)), (4_097, (3,) * 7), (2_051, (3,) * 11), (1_027, (2, 3))])
 def test_factored_sh_gradient_is_the_sum_of_the_views(P, degrees):
     """View-parallel exchange (csrc/sh_views.cu): the backward asked for the factored SH gradient leaves dL_dRGB + the camera
-    centre (and every other output unchanged); gof_sh_grad_from_views over three views' records is BIT-identical to adding the
-    three dL_dsh tensors of the plain backward in view order (backward.cu:45-139 is an outer product per view)."""
+    centre (and every other output unchanged); gof_sh_grad_from_views over the views' records is BIT-identical to adding the
+    views' dL_dsh tensors of the same backward runs in view order (backward.cu:45-139 is an outer product per view)."""
     import ctypes
     from diff_gaussian_rasterization import _C
     import gof_dp
     dev = torch.device("cuda")
     H, W = 208, 320
     slot = gof_dp.SH_SLOT_HEADER + (3 * P + 63) // 64 * 64
-    records = torch.full((3 * slot,), float("nan"), device=dev)
+    nv = len(degrees)                                  # 2 / 3 / 7 / 11 views: every instantiation of the expansion kernel
+    records = torch.full((nv * slot,), float("nan"), device=dev)
     grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(2)).to(dev)
     want, means = None, None
-    for i, (view, deg) in enumerate(zip((4, 11, 23), degrees)):
+    for i, (view, deg) in enumerate(zip([(4 + 7 * j) % 64 for j in range(nv)], degrees)):
         cam, gs = gof_synth.make_scene(dict(P=P, width=W, height=H, seed=17), view=view)
         fa = _util.fwd_args(cam, gs, dev, sh_degree=deg)
         R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
@@ -159,13 +160,13 @@ def test_factored_sh_gradient_is_the_sum_of_the_views(P, degrees):
         want = full.clone() if want is None else want + full
         means = fa[1]
     got = torch.full((P, 16, 3), float("nan"), device=dev)
-    ptrs = (ctypes.c_void_p * 3)(*[records.data_ptr() + 4 * i * slot for i in range(3)])
-    _C._check(_C._lib.gof_sh_grad_from_views(P, 16, 3, means.data_ptr(), ptrs, got.data_ptr(), _C._stream()))
+    ptrs = (ctypes.c_void_p * nv)(*[records.data_ptr() + 4 * i * slot for i in range(nv)])
+    _C._check(_C._lib.gof_sh_grad_from_views(P, 16, nv, means.data_ptr(), ptrs, got.data_ptr(), _C._stream()))
     torch.cuda.synchronize()
     assert float(want.abs().max()) > 0
     assert torch.equal(got, want)
     # ... and the torch statement of the same sum (the CPU buckets of the gloo tests) agrees to rounding
-    ref = gof_dp.sh_grad_from_views_torch(means, [records[i * slot:(i + 1) * slot] for i in range(3)], P, 16)
+    ref = gof_dp.sh_grad_from_views_torch(means, [records[i * slot:(i + 1) * slot] for i in range(nv)], P, 16)
     assert _util.rel_err(ref, want)[0] < 1e-5
 
 
