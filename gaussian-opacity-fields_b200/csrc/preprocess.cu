@@ -239,8 +239,9 @@ struct PreBwdArgs {
   float* dL_dcov3D;         // optional [P][6]: written as zeros
   float* dens_sum;          // optional [P][3]: |dL_dmean2D.xy|, |dL_dmean2D.z|, 1 for visible Gaussians (gof_rasterize_backward_stats)
   float* dens_max;          // optional [P][2]: |dL_dmean2D.z|, radius
-  float* sh_rgb;            // optional [P][3]: the clamp-masked dL_dRGB the SH gradient is the outer product of (view-parallel exchange,
-  float* sh_hdr;            //   csrc/sh_views.cu); sh_hdr[0..3] = camera centre, active degree.  dL_dsh may then be NULL.
+  float* sh_rgb;            // optional [3][GOF_SH_PLANE(P)] planes: the clamp-masked dL_dRGB the SH gradient is the outer product of
+  float* sh_hdr;            //   (view-parallel exchange, csrc/sh_views.cu); sh_hdr[0..3] = camera centre, active degree.  dL_dsh may be NULL.
+  size_t sh_plane;
 };
 
 // m[c][r] column-major helpers mirroring the glm products used by backward.cu:381-587.  The chain rule through
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
       a.dL_dmean3D[3 * (size_t)idx + c] = 0.f;
     }
     a.dL_dopacity[idx] = 0.f;
-    if (a.sh_rgb != nullptr) { a.sh_rgb[3 * (size_t)idx] = 0.f; a.sh_rgb[3 * (size_t)idx + 1] = 0.f; a.sh_rgb[3 * (size_t)idx + 2] = 0.f; }
+    if (a.sh_rgb != nullptr) { a.sh_rgb[idx] = 0.f; a.sh_rgb[a.sh_plane + idx] = 0.f; a.sh_rgb[2 * a.sh_plane + idx] = 0.f; }
     if (a.dens_sum != nullptr) {
       a.dens_sum[3 * (size_t)idx] = 0.f; a.dens_sum[3 * (size_t)idx + 1] = 0.f; a.dens_sum[3 * (size_t)idx + 2] = 0.f;
       a.dens_max[2 * (size_t)idx] = 0.f; a.dens_max[2 * (size_t)idx + 1] = 0.f;
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(K8_THREADS) k_preprocess_backward(const PreBwd
 
     float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
 #define SH(k, c) sh[3 * (k) + (c)]
-    if (a.sh_rgb != nullptr) { a.sh_rgb[3 * (size_t)idx] = dRGB[0]; a.sh_rgb[3 * (size_t)idx + 1] = dRGB[1]; a.sh_rgb[3 * (size_t)idx + 2] = dRGB[2]; }
+    if (a.sh_rgb != nullptr) { a.sh_rgb[idx] = dRGB[0]; a.sh_rgb[a.sh_plane + idx] = dRGB[1]; a.sh_rgb[2 * a.sh_plane + idx] = dRGB[2]; }
     if (a.dL_dsh != nullptr) {
       float w[16];
       gof_sh_grad_weights(a.D, x, y, z, w);
@@ -619,7 +620,7 @@ int gof_launch_preprocess_backward(const gof_scene_t* s, const GofView& v, const
   a.dL_dcolor = dL_dcolor; a.dL_dv2g = dL_dv2g; a.dL_dmean3D = dL_dmean3D; a.dL_dsh = dL_dsh;
   a.dL_dscale = dL_dscale; a.dL_drot = dL_drot; a.dL_dcov3D = dL_dcov3D;
   a.dens_sum = (dens_sum && dens_max) ? dens_sum : nullptr; a.dens_max = a.dens_sum ? dens_max : nullptr;
-  a.sh_rgb = s->shs ? sh_rgb : nullptr; a.sh_hdr = a.sh_rgb ? sh_hdr : nullptr;
+  a.sh_rgb = s->shs ? sh_rgb : nullptr; a.sh_hdr = a.sh_rgb ? sh_hdr : nullptr; a.sh_plane = GOF_SH_PLANE(s->P);
   GOF_LAUNCH("preprocess_bwd", st, k_preprocess_backward<<<(s->P + K8_THREADS - 1) / K8_THREADS, K8_THREADS, 0, st>>>(a));
   GOF_LAUNCH_CHECK(s->debug, st);
   return GOF_OK;

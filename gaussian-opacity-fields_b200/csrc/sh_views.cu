@@ -37,14 +37,17 @@ __global__ void __launch_bounds__(SHV_THREADS) k_sh_grad_from_views(const ShvArg
   float acc[48];
 #pragma unroll
   for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+  const size_t plane = GOF_SH_PLANE(a.P);
   if (idx < a.P) {
     float rgb[NV][3];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       rgb[v][0] = rgb[v][1] = rgb[v][2] = 0.f;
       if (v < a.n_views) {
-        const float* p = a.slot[v] + GOF_SH_SLOT_HEADER + 3 * (size_t)idx;
-        rgb[v][0] = __ldcg(p); rgb[v][1] = __ldcg(p + 1); rgb[v][2] = __ldcg(p + 2);   // L2 only: may be a peer's memory
+        // three colour PLANES: a warp's load is one contiguous 128 bytes.  (Interleaved [P][3] records made every scalar load
+        // touch all twelve sectors of the warp's 384 bytes -- three times the NVLink traffic when the record is a peer's.)
+        const float* p = a.slot[v] + GOF_SH_SLOT_HEADER + idx;
+        rgb[v][0] = __ldcg(p); rgb[v][1] = __ldcg(p + plane); rgb[v][2] = __ldcg(p + 2 * plane);   // L2 only: may be a peer's memory
       }
     }
     const float mx = a.means3D[3 * (size_t)idx], my = a.means3D[3 * (size_t)idx + 1], mz = a.means3D[3 * (size_t)idx + 2];

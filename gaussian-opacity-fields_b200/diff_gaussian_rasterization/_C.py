@@ -256,7 +256,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     # contiguous, 256-byte aligned view of the block.
     shapes = dict(dmeans3D=(P, 3), dmeans2D=(P, 3), dcolors=(P, 3), dopacity=(P, 1), dcov3D=(P, 6), dsh=(P, M, 3),
                   dscales=(P, 3), drot=(P, 4), dv2g=(P, 10))
-    # `_out` with "dsh_rgb" (P,3) + "sh_hdr" (>= 4 floats): the factored SH gradient of view-parallel training (gof_dp.GradBucket,
+    # `_out` with "dsh_rgb" (3, GOF_SH_PLANE(P)) + "sh_hdr" (>= 4 floats): the factored SH gradient of view-parallel training (gof_dp.GradBucket,
     # csrc/sh_views.cu) -- the backward leaves the clamp-masked dL_dRGB and the camera centre instead of dL_dsh, which only exists
     # after the bucket's exchange (the returned dL_dsh is then _out.get("dsh"): the tensor the exchange fills)
     factored = _out is not None and "dsh_rgb" in _out
@@ -264,9 +264,11 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         rgb_t, hdr_t = _out["dsh_rgb"], _out.get("sh_hdr")
         if sh is None or sh.numel() == 0:
             raise RuntimeError("gof_b200: the factored SH gradient (_out['dsh_rgb']) needs SH input")
-        if hdr_t is None or not (rgb_t.is_contiguous() and hdr_t.is_contiguous() and tuple(rgb_t.shape) == (P, 3) and hdr_t.numel() >= 4
+        plane = (P + 63) // 64 * 64          # GOF_SH_PLANE(P)
+        if hdr_t is None or not (rgb_t.is_contiguous() and hdr_t.is_contiguous() and tuple(rgb_t.shape) == (3, plane) and hdr_t.numel() >= 4
                                  and rgb_t.dtype == torch.float32 and hdr_t.dtype == torch.float32):
-            raise RuntimeError("gof_b200: _out['dsh_rgb'] must be a contiguous float32 (P,3) tensor and _out['sh_hdr'] hold >= 4 floats")
+            raise RuntimeError(f"gof_b200: _out['dsh_rgb'] must be a contiguous float32 (3, {plane}) tensor (three colour planes of "
+                               "GOF_SH_PLANE(P) floats) and _out['sh_hdr'] hold >= 4 floats")
         _out["_means3D"] = means3D if means3D.is_contiguous() else means3D.contiguous()
         full_t = _out.get("_dsh_full")      # checks only: ALSO write this view's own dL_dsh (P,M,3), from the same dL_dRGB
         if full_t is not None and not (full_t.is_contiguous() and tuple(full_t.shape) == (P, M, 3) and full_t.dtype == torch.float32

@@ -18,7 +18,7 @@ Factored SH gradient (`GradBucket(..., factor_sh=True)`): 48 of the 59 gradient 
 dL_dsh is an outer product w(dir(mean, camera)) (x) dL_dRGB (backward.cu:45-139).  Every rank holds all means, so the ranks only
 need each other's clamp-masked dL_dRGB -- 3 floats per Gaussian and view -- and each expands sum_v w(dir_v) (x) rgb_v itself
 (csrc/sh_views.cu), in rank order, bit-identical to adding the views' dL_dsh tensors.  The reduced part of the bucket shrinks from
-64 to 16 floats per Gaussian; the per-view records sit behind it ([world] x (64-float header + [P,3])) and are read in place over
+64 to 16 floats per Gaussian; the per-view records sit behind it ([world] x (64-float header + three colour planes)) and are read in place over
 NVLink by the expansion kernel (peer-memory / NVLS exchange) or all-gathered (NCCL / gloo).
 
 The bucket also carries this view's densification statistics (written by the rasterizer backward itself, see
@@ -75,7 +75,8 @@ class GradBucket:
         self._slot = 0
         self.dsh = None
         if self.factored:    # [n_reduce, numel): one record per view = SH_SLOT_HEADER floats (camera centre, degree) + rgb [P,3]
-            self._slot = SH_SLOT_HEADER + (self.P * 3 + 63) // 64 * 64
+            self._plane = (self.P + 63) // 64 * 64          # GOF_SH_PLANE(P): the record's three colour planes
+            self._slot = SH_SLOT_HEADER + 3 * self._plane
             off += self._n_views * self._slot
             self.dsh = torch.zeros(self.P, self.M, 3, dtype=dtype, device=device)
         self.numel = off
@@ -94,7 +95,7 @@ class GradBucket:
         if self.factored:
             rec = self._record(self._view)
             views["sh_hdr"] = rec[:SH_SLOT_HEADER]
-            views["dsh_rgb"] = rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P].view(self.P, 3)
+            views["dsh_rgb"] = rec[SH_SLOT_HEADER:].view(3, self._plane)
             views["dsh"] = self.dsh
         return views
 
@@ -346,8 +347,8 @@ class GradBucket:
             if self.factored:
                 rec = self._record(self._view)
                 rec[:4] = torch.tensor([0.3 * self._view - 0.5, 0.25, -3.0, 3.0], device=dev)
-                rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P].normal_()
-                rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P:7] = 0.0
+                rec[SH_SLOT_HEADER:].normal_()
+                rec[SH_SLOT_HEADER:].view(3, self._plane)[:, ::7] = 0.0
                 self.views["_means3D"] = means
         for mode in modes:
             try:
@@ -393,9 +394,9 @@ class GradBucket:
         rec = self._record(rank)
         rec.zero_()
         rec[:4] = torch.tensor([0.3 * rank - 0.5, 0.25, -3.0 - 0.1 * rank, 3.0], device=dev)
-        rgb = torch.randn(self.P, 3, generator=torch.Generator().manual_seed(77 + rank)).to(dev)
-        rgb[rank::5] = 0.0
-        rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * self.P] = rgb.reshape(-1)
+        rgb = torch.randn(3, self._plane, generator=torch.Generator().manual_seed(77 + rank)).to(dev)
+        rgb[:, rank::5] = 0.0
+        rec[SH_SLOT_HEADER:] = rgb.reshape(-1)
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
         self._expand_sh(self._record_ptrs(), means)
@@ -494,11 +495,12 @@ def sh_grad_weights_torch(dirs, degree):
 
 
 def sh_grad_from_views_torch(means3D, records, P, M):
-    """sum_v w(dir(means3D, camera_v)) (x) rgb_v as [P,M,3] from view records (header: camera centre, degree | rgb [P,3])."""
+    """sum_v w(dir(means3D, camera_v)) (x) rgb_v as [P,M,3] from view records (header: camera centre, degree | rgb planes [3][plane])."""
     out = torch.zeros(P, M, 3, dtype=means3D.dtype, device=means3D.device)
     for rec in records:
         cam, degree = rec[:3], int(round(float(rec[3])))
-        rgb = rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * P].view(P, 3)
+        plane = (P + 63) // 64 * 64
+        rgb = rec[SH_SLOT_HEADER:SH_SLOT_HEADER + 3 * plane].view(3, plane)[:, :P].t()
         d = means3D - cam[None, :]
         d = d / torch.linalg.vector_norm(d, dim=1, keepdim=True)
         w = sh_grad_weights_torch(d, degree)

@@ -117,8 +117,10 @@ GOF_API int gof_rasterize_backward_stats(const gof_scene_t* scene, int num_rende
  * single-GPU).  The SH gradient of ONE view is an outer product: dL_dsh[g][k][c] = w_k(dir(mean_g, camera)) * dL_dRGB[g][c]
  * (backward.cu:45-139), so the ranks exchange the 3 floats of the clamp-masked dL_dRGB per Gaussian and view instead of the
  * 48 of dL_dsh and every rank expands the sum over the views itself (gof_sh_grad_from_views).
- * gof_rasterize_backward_dp = gof_rasterize_backward_stats that additionally writes sh_rgb [P,3] (zeros for invisible
- * Gaussians) and sh_hdr[0..3] = camera centre, active SH degree; with both given dL_dsh may be NULL (it is then not computed). */
+ * gof_rasterize_backward_dp = gof_rasterize_backward_stats that additionally writes sh_rgb -- three colour planes
+ * [3][GOF_SH_PLANE(P)], zeros for invisible Gaussians -- and sh_hdr[0..3] = camera centre, active SH degree; with both given
+ * dL_dsh may be NULL (it is then not computed). */
+#define GOF_SH_PLANE(P) ((((size_t)(P)) + 63u) / 64u * 64u)
 GOF_API int gof_rasterize_backward_dp(const gof_scene_t* scene, int num_rendered, const int* radii, void* geom_buffer,
                            const void* binning_buffer, const void* image_buffer, const float* dL_dpix, float* dL_dmean2D,
                            float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
@@ -126,7 +128,7 @@ GOF_API int gof_rasterize_backward_dp(const gof_scene_t* scene, int num_rendered
                            float* dens_max, float* sh_rgb, float* sh_hdr, void* stream);
 /* dL_dsh [P,M,3] = sum over v = 0..n_views-1, in that order, of w(dir(means3D, camera_v)) (x) rgb_v, bit-identical to adding the
  * views' own dL_dsh in that order; coefficients above the active degree are written as zeros.  slots[v] points to view v's
- * record: 64 floats of header (sh_hdr as written by gof_rasterize_backward_dp) followed by rgb [P,3]; the pointers may address
+ * record: 64 floats of header (sh_hdr as written by gof_rasterize_backward_dp) followed by the planes [3][GOF_SH_PLANE(P)]; the pointers may address
  * peer GPUs' memory (NVLink): the records are then read where the ranks left them, without a gather step. */
 #define GOF_SH_SLOT_HEADER 64
 GOF_API int gof_sh_grad_from_views(int P, int M, int n_views, const float* means3D, const float* const* slots, float* dL_dsh,

@@ -116,7 +116,8 @@ def _worker_factored(rank, world, port, q):
     P, M = 203, 16
     b = gof_dp.GradBucket(P, M, "cpu", factor_sh=True)
     assert "dsh_rgb" in b.views and b.views["dsh"].shape == (P, M, 3) and b.n_reduce == b.n_sum + 2 * P // 64 * 64 + 64 * (2 * P % 64 != 0)
-    assert b.numel == b.n_reduce + world * (64 + (3 * P + 63) // 64 * 64)
+    plane = (P + 63) // 64 * 64
+    assert b.numel == b.n_reduce + world * (64 + 3 * plane) and b.views["dsh_rgb"].shape == (3, plane)
     g = torch.Generator().manual_seed(10 + rank)
     means = torch.randn(P, 3, generator=torch.Generator().manual_seed(5)) * 2     # the same Gaussians on every rank
     cam = torch.tensor([3.0 + rank, -1.0, 0.5 * rank])
@@ -125,8 +126,9 @@ def _worker_factored(rank, world, port, q):
     for name in ("dmeans3D", "dopacity", "dscales", "drot", "dens_sum", "dens_max", "dsh_rgb"):
         b.views[name].copy_(torch.randn(b.views[name].shape, generator=g))
         local[name] = b.views[name].clone()
-    b.views["dsh_rgb"][::3] = 0.0
-    local["dsh_rgb"] = b.views["dsh_rgb"].clone()
+    b.views["dsh_rgb"][:, ::3] = 0.0
+    b.views["dsh_rgb"][:, P:] = 0.0
+    local["dsh_rgb"] = b.views["dsh_rgb"][:, :P].t().contiguous()        # (P,3)
     b.views["sh_hdr"][:4] = torch.tensor([cam[0], cam[1], cam[2], float(degree)])
     b.all_reduce(means3D=means)
     q.put((rank, {k: v.numpy().copy() for k, v in local.items()}, {k: v.numpy().copy() for k, v in b.views.items()},

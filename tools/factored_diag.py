@@ -17,7 +17,8 @@ from diff_gaussian_rasterization import _C  # noqa: E402
 
 dev = torch.device("cuda")
 P, H, W = 30_011, 208, 320
-slot = gof_dp.SH_SLOT_HEADER + (3 * P + 63) // 64 * 64
+plane = (P + 63) // 64 * 64
+slot = gof_dp.SH_SLOT_HEADER + 3 * plane
 records = torch.zeros(3 * slot, device=dev)
 grad = torch.randn(9, H, W, generator=torch.Generator().manual_seed(2)).to(dev)
 fulls, means = [], None
@@ -27,7 +28,7 @@ for i, view in enumerate((4, 11, 23)):
     R, color, radii, geom, binning, img = _C.rasterize_gaussians(*fa)
     rec = records[i * slot:(i + 1) * slot]
     full = torch.full((P, 16, 3), float("nan"), device=dev)
-    out = {"sh_hdr": rec[:64], "dsh_rgb": rec[64:64 + 3 * P].view(P, 3), "_dsh_full": full}
+    out = {"sh_hdr": rec[:64], "dsh_rgb": rec[64:].view(3, plane), "_dsh_full": full}
     fact = _C.rasterize_gaussians_backward(*_util.bwd_args(fa, radii, geom, R, binning, img, grad), _out=out)
     torch.cuda.synchronize()
     means = fa[1]
@@ -45,7 +46,7 @@ for i, view in enumerate((4, 11, 23)):
     bad = (got != full).nonzero()
     if len(bad):
         g, k, c = [int(t) for t in bad[0]]
-        print("   first mismatch", (g, k, c), float(got[g, k, c]), float(full[g, k, c]), "rgb", out["dsh_rgb"][g].tolist(), "radius", int(radii[g]))
+        print("   first mismatch", (g, k, c), float(got[g, k, c]), float(full[g, k, c]), "rgb", out["dsh_rgb"][:, g].tolist(), "radius", int(radii[g]))
 want = (fulls[0] + fulls[1]) + fulls[2]
 got = torch.full((P, 16, 3), float("nan"), device=dev)
 ptrs = (ctypes.c_void_p * 3)(*[records.data_ptr() + 4 * i * slot for i in range(3)])
