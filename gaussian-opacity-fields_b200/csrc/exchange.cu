@@ -1,6 +1,7 @@
-// exchange.cu -- the one exchange step of view-parallel training: the sum over ranks of the flat
-// per-Gaussian gradient bucket (59 floats per Gaussian), done by ONE kernel over NVLink peer memory instead of a
-// library all-reduce.  No reference counterpart (the reference is single-GPU).
+// exchange.cu -- the reduction of the one exchange step of view-parallel training: the sum over ranks of the flat
+// per-Gaussian gradient bucket -- 59 gradient + 5 statistics floats per Gaussian, or 11 + 5 when the SH gradient travels as
+// per-view dL_dRGB records (gof_dp.GradBucket(factor_sh=True), csrc/sh_views.cu) -- done by ONE kernel over NVLink peer memory
+// or through the NVSwitch instead of a library all-reduce.  No reference counterpart (the reference is single-GPU).
 //
 // Every rank's bucket is mapped into every process (CUDA IPC).  Rank r owns the r-th 1/N slice of the index space:
 // it loads that slice from all N buckets (N-1 of them over NVLink), adds them in rank order 0..N-1 -- so every rank
